@@ -1,0 +1,66 @@
+"""Builds libchemsim_lbm.so (the C-ABI library) in-tree with nvcc for sm_100a.
+
+    python -m chemsim_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU
+box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libchemsim_lbm.so")
+SOURCES = ["kernels.cu", "lattice.cu"]
+HEADERS = ["d2q9.cuh", "kernels.cuh", "nccl_dyn.h", os.path.join("..", "..", "include", "chemsim_lbm.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                      # parity build: never contract a*b+c (d2q9.cuh also uses *_rn intrinsics)
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
+    "-Xptxas", "-v",
+    "-cudart", "static",
+    "-shared",
+]
+
+
+def nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", "g++", "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    env = dict(os.environ)
+    env["PATH"] = "/usr/bin:" + env.get("PATH", "")     # plain system g++ as nvcc's host compiler
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + log)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + log)
+    if verbose:
+        print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

@@ -1,0 +1,130 @@
+// d2q9.cuh — D2Q9 tables and the per-cell arithmetic shared by every kernel.
+//
+// The arithmetic restates /root/reference/src/lbm.rs in the reference's exact
+// operation order.  Every floating-point operation goes through
+// an explicit round-to-nearest intrinsic (__fadd_rn, __dmul_rn, ...), which the
+// compiler never contracts into an FMA, so results are bit-identical to an IEEE
+// evaluation of the reference's expression tree (ArrayFire's CPU backend).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace chemsim {
+
+constexpr int Q = 9;
+
+// Lattice velocities c_i (src/lbm.rs:221-231).
+__host__ __device__ constexpr int cx_of(int i) { return i == 1 || i == 5 || i == 8 ? 1 : (i == 3 || i == 6 || i == 7 ? -1 : 0); }
+__host__ __device__ constexpr int cy_of(int i) { return i == 2 || i == 5 || i == 6 ? 1 : (i == 4 || i == 7 || i == 8 ? -1 : 0); }
+// State::stream (src/lbm.rs:716-729): convolve2 with stencil_i^T moves population
+// i by (dy, dx) = (-c_ix, +c_iy) in [y][x] memory terms.
+__host__ __device__ constexpr int ey_of(int i) { return -cx_of(i); }
+__host__ __device__ constexpr int ex_of(int i) { return cy_of(i); }
+// D2Q9::swap_populations (src/lbm.rs:298-309).
+__host__ __device__ constexpr int opp_of(int i) { return i == 0 ? 0 : (i <= 4 ? ((i + 1) % 4) + 1 : ((i - 3) % 4) + 5); }
+static_assert(opp_of(1) == 3 && opp_of(2) == 4 && opp_of(3) == 1 && opp_of(4) == 2, "opp");
+static_assert(opp_of(5) == 7 && opp_of(6) == 8 && opp_of(7) == 5 && opp_of(8) == 6, "opp");
+
+// Host scalars, computed on the host in T exactly as the reference does
+// (src/lbm.rs:54-56, :64-66, :84, :209-219, :357).
+template <typename T>
+struct Consts {
+    T w[Q];    // 16/36, 4/36 x4, 1/36 x4
+    T cs2;     // cs*cs, cs = dx/(sqrt(3)*dt)
+    T k1;      // 1/cs2
+    T k2;      // 1/(2*cs4)
+    T k3;      // -1/(2*cs2)
+    T factor;  // BGK: -dt/tau
+};
+
+// ---- rounded, never-contracted arithmetic -----------------------------------
+__device__ __forceinline__ float  add(float a, float b)   { return __fadd_rn(a, b); }
+__device__ __forceinline__ float  sub(float a, float b)   { return __fsub_rn(a, b); }
+__device__ __forceinline__ float  mul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ float  divi(float a, float b)  { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float  root(float a)           { return __fsqrt_rn(a); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double divi(double a, double b){ return __ddiv_rn(a, b); }
+__device__ __forceinline__ double root(double a)          { return __dsqrt_rn(a); }
+
+// Macroscopic moments of one cell, in the reference's order.
+template <typename T>
+struct Moments { T rho, mx, my, vx, vy; };
+
+// Lattice::density (src/lbm.rs:117-121): ((0 + f0) + f1) + ... + f8
+template <typename T>
+__device__ __forceinline__ T density(const T (&g)[Q])
+{
+    T rho = T(0);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) rho = add(rho, g[i]);
+    return rho;
+}
+
+// Lattice::momentum_density (src/lbm.rs:123-131): md = md + f_i * c_i, every
+// product formed (including *0 and *-1).
+template <typename T>
+__device__ __forceinline__ void momentum(const T (&g)[Q], T &mx, T &my)
+{
+    mx = T(0); my = T(0);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        mx = add(mx, mul(g[i], T(cx_of(i))));
+        my = add(my, mul(g[i], T(cy_of(i))));
+    }
+}
+
+// Lattice::velocity (src/lbm.rs:133-138; Matrix::recip src/matrix.rs:133-136):
+// r = 1/rho, v = r * m.
+template <typename T>
+__device__ __forceinline__ Moments<T> moments(const T (&g)[Q])
+{
+    Moments<T> m;
+    m.rho = density(g);
+    momentum(g, m.mx, m.my);
+    const T r = divi(T(1), m.rho);
+    m.vx = mul(r, m.mx);
+    m.vy = mul(r, m.my);
+    return m;
+}
+
+// compute_equilibrium for one direction (src/lbm.rs:58-68).
+template <typename T>
+__device__ __forceinline__ T equilibrium_i(int i, T rho, T vx, T vy, T v2, const Consts<T> &k)
+{
+    const T vc  = add(mul(vx, T(cx_of(i))), mul(vy, T(cy_of(i))));
+    const T vc2 = mul(vc, vc);
+    const T sum = add(add(add(T(1), mul(vc, k.k1)), mul(vc2, k.k2)), mul(v2, k.k3));
+    return mul(mul(rho, k.w[i]), sum);
+}
+
+// State::collide with BGK (src/lbm.rs:731-739, :349-364): g <- g + (g - feq)*factor
+template <typename T>
+__device__ __forceinline__ void collide_bgk(T (&g)[Q], const Consts<T> &k)
+{
+    const Moments<T> m = moments(g);
+    const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));   // src/lbm.rs:53
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const T fe = equilibrium_i(i, m.rho, m.vx, m.vy, v2, k);
+        g[i] = add(g[i], mul(sub(g[i], fe), k.factor));
+    }
+}
+
+// State::bounce_back (src/lbm.rs:741-751): g_i <- solid ? g_opp(i) : g_i
+template <typename T>
+__device__ __forceinline__ void bounce_back(T (&g)[Q], bool solid)
+{
+    if (solid) {
+        T t;
+        t = g[1]; g[1] = g[3]; g[3] = t;
+        t = g[2]; g[2] = g[4]; g[4] = t;
+        t = g[5]; g[5] = g[7]; g[7] = t;
+        t = g[6]; g[6] = g[8]; g[8] = t;
+    }
+}
+
+}  // namespace chemsim

@@ -1,0 +1,416 @@
+// kernels.cu — sm_100a kernels of the D2Q9 path.
+//
+//  step_vec_kernel     the hot path: ONE pass per time step that pull-streams the
+//                      nine populations (State::stream, src/lbm.rs:716-729),
+//                      reverses them on solid cells (State::bounce_back, :741-751)
+//                      and relaxes them (State::collide + BGK, :731-739, :349-364),
+//                      with 128-bit loads/stores over the SoA layout.
+//  step_scalar_kernel  the same update, one cell per thread, for widths that are
+//                      not a multiple of the vector width.
+//  readout / mass / unstable / init kernels for the macroscopic surface of
+//                      lbm.rs (:117-160, :779-818, :43-71).
+//
+// HBM-bound integer-free streaming work: no tensor cores, no shared-memory
+// tiling (every population value is read once and written once per step).
+#include "kernels.cuh"
+
+namespace chemsim {
+
+namespace {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float>  { using type = float4;  static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+
+__device__ __forceinline__ void load_vec(const float *p, float (&v)[4])
+{
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load_vec(const double *p, double (&v)[2])
+{
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_vec(double *p, const double (&v)[2])
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+}
+__device__ __forceinline__ void load_mask(const uint8_t *p, bool (&s)[4])
+{
+    const uchar4 t = *reinterpret_cast<const uchar4 *>(p);
+    s[0] = t.x != 0; s[1] = t.y != 0; s[2] = t.z != 0; s[3] = t.w != 0;
+}
+__device__ __forceinline__ void load_mask(const uint8_t *p, bool (&s)[2])
+{
+    const uchar2 t = *reinterpret_cast<const uchar2 *>(p);
+    s[0] = t.x != 0; s[1] = t.y != 0;
+}
+
+constexpr int STEP_THREADS = 256;
+
+// ---- the fused step, vector form ---------------------------------------------
+// Thread (tx, ty) of block (bx, by) updates the V = 16/sizeof(T) cells
+// x0 … x0+V−1 of row y.  blockDim.x is a multiple of 32, so a warp always lies
+// inside one row and the two neighbouring lanes hold the neighbouring vectors:
+// populations that stream along x (dx = ±1) are assembled from the thread's own
+// aligned vector plus ONE element shuffled in from the adjacent lane; only the
+// first/last lane of a warp (or of the row) issues an extra scalar load, which
+// also implements the x edge (wrap or zero-fill).
+template <typename T, bool PERIODIC_X, bool HAS_MASK>
+__global__ void __launch_bounds__(STEP_THREADS)
+step_vec_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    constexpr int V = VecOf<T>::N;
+    const int y = a.y_begin + blockIdx.x * blockDim.y + threadIdx.y;
+    if (y >= a.y_end) return;                        // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int xv = blockIdx.y * blockDim.x + threadIdx.x;
+    const int nvec = a.W / V;
+    const bool active = xv < nvec;
+    const int x0 = xv * V;
+
+    T g[Q][V];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        int sy = y - ey_of(q);
+        if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
+        const T *row = a.src + (size_t)q * a.plane + (size_t)(sy + 1) * a.pitch;
+        T v[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = T(0);
+        if (active) load_vec(row + x0, v);
+        if (ex_of(q) == 0) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) g[q][j] = v[j];
+        } else if (ex_of(q) == 1) {                  // value at x comes from x−1
+            T left = __shfl_up_sync(0xffffffffu, v[V - 1], 1);
+            if (active && (lane == 0 || xv == 0)) {
+                if (xv > 0) left = row[x0 - 1];
+                else left = PERIODIC_X ? row[a.W - 1] : T(0);
+            }
+            g[q][0] = left;
+#pragma unroll
+            for (int j = 1; j < V; ++j) g[q][j] = v[j - 1];
+        } else {                                     // value at x comes from x+1
+            T right = __shfl_down_sync(0xffffffffu, v[0], 1);
+            if (active && (lane == 31 || xv == nvec - 1)) {
+                if (xv < nvec - 1) right = row[x0 + V];
+                else right = PERIODIC_X ? row[0] : T(0);
+            }
+#pragma unroll
+            for (int j = 0; j < V - 1; ++j) g[q][j] = v[j + 1];
+            g[q][V - 1] = right;
+        }
+    }
+    if (!active) return;
+
+    bool solid[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) solid[j] = false;
+    if (HAS_MASK) load_mask(a.mask + (size_t)y * a.mask_pitch + x0, solid);
+
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        T c[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) c[q] = g[q][j];
+        if (HAS_MASK) bounce_back(c, solid[j]);
+        collide_bgk(c, a.k);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[q][j] = c[q];
+    }
+
+    T *out = a.dst + (size_t)(y + 1) * a.pitch + x0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) store_vec(out + (size_t)q * a.plane, g[q]);
+}
+
+// ---- the fused step, one cell per thread (any width) -------------------------
+template <typename T>
+__global__ void __launch_bounds__(STEP_THREADS)
+step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    const int x = blockIdx.y * blockDim.x + threadIdx.x;
+    const int y = a.y_begin + blockIdx.x * blockDim.y + threadIdx.y;
+    if (y >= a.y_end || x >= a.W) return;
+    T c[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        int sy = y - ey_of(q);
+        if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
+        int sx = x - ex_of(q);
+        bool inside = true;
+        if (sx < 0)         { if (a.periodic_x) sx = a.W - 1; else inside = false; }
+        else if (sx >= a.W) { if (a.periodic_x) sx = 0;       else inside = false; }
+        c[q] = inside ? a.src[(size_t)q * a.plane + (size_t)(sy + 1) * a.pitch + sx] : T(0);
+    }
+    if (a.has_mask) bounce_back(c, a.mask[(size_t)y * a.mask_pitch + x] != 0);
+    collide_bgk(c, a.k);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) a.dst[(size_t)q * a.plane + (size_t)(y + 1) * a.pitch + x] = c[q];
+}
+
+// ---- compute_equilibrium on the device (src/lbm.rs:43-71) --------------------
+template <typename T>
+__global__ void init_equilibrium_kernel(const T *rho, const T *vx, const T *vy, T *dst, size_t plane, int pitch,
+                                        int W, int H, const __grid_constant__ Consts<T> k)
+{
+    const int x = blockIdx.y * blockDim.x + threadIdx.x;
+    const int y = blockIdx.x;
+    if (x >= W || y >= H) return;
+    const size_t c = (size_t)y * W + x;
+    const T r = rho[c], ux = vx[c], uy = vy[c];
+    const T v2 = add(mul(ux, ux), mul(uy, uy));
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+        dst[(size_t)q * plane + (size_t)(y + 1) * pitch + x] = equilibrium_i(q, r, ux, uy, v2, k);
+}
+
+// ---- macroscopic readout (src/lbm.rs:117-173, :779-812) ----------------------
+template <typename T>
+__global__ void readout_kernel(const __grid_constant__ ReadoutArgs<T> a)
+{
+    const int x = blockIdx.y * blockDim.x + threadIdx.x;
+    const int y = blockIdx.x;
+    if (x >= a.W || y >= a.H) return;
+    T g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) g[q] = a.src[(size_t)q * a.plane + (size_t)(y + 1) * a.pitch + x];
+    const size_t c = (size_t)y * a.W + x;
+    switch (a.kind) {
+    case READ_DENSITY:  a.out0[c] = density(g); break;
+    case READ_PRESSURE: a.out0[c] = mul(density(g), a.k.cs2); break;       // :784-787
+    case READ_MOMENTUM: { T mx, my; momentum(g, mx, my); a.out0[c] = mx; a.out1[c] = my; break; }
+    case READ_VELOCITY: { const Moments<T> m = moments(g); a.out0[c] = m.vx; a.out1[c] = m.vy; break; }
+    case READ_SPEED: {                                                      // :151-154
+        const Moments<T> m = moments(g);
+        a.out0[c] = root(add(mul(m.vx, m.vx), mul(m.vy, m.vy)));
+        break;
+    }
+    case READ_EQUILIBRIUM:
+    case READ_NON_EQUILIBRIUM: {                                            // :156-173
+        const Moments<T> m = moments(g);
+        const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));
+        T fe = T(0), f = T(0);
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            if (q == a.q) { fe = equilibrium_i(q, m.rho, m.vx, m.vy, v2, a.k); f = g[q]; }
+        a.out0[c] = (a.kind == READ_EQUILIBRIUM) ? fe : sub(f, fe);
+        break;
+    }
+    }
+}
+
+// ---- reductions: warp shuffle -> block -> per-block partial -> final block ----
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 148 * 8;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double warp_part[RED_THREADS / 32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < RED_THREADS / 32 ? warp_part[threadIdx.x] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;   // valid in thread 0
+}
+
+// total mass: every population of every cell, accumulated in f64
+// (Matrix::sum -> af::sum_all, src/matrix.rs:138-140)
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+mass_partial_kernel(const T *src, size_t plane, int pitch, int W, int H, double *partials)
+{
+    double acc = 0.0;
+    const size_t cells = (size_t)W * H;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(c / W), x = (int)(c % W);
+        const T *p = src + (size_t)(y + 1) * pitch + x;
+        double cell = 0.0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) cell += (double)p[(size_t)q * plane];
+        acc += cell;
+    }
+    const double b = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+mass_final_kernel(const double *partials, int n, double *out)
+{
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];   // fixed order: deterministic
+    const double b = block_sum(acc);
+    if (threadIdx.x == 0) *out = b;
+}
+
+// State::is_unstable (src/lbm.rs:815-818): any f_eq,0 < 0
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+unstable_kernel(const T *src, size_t plane, int pitch, int W, int H, const __grid_constant__ Consts<T> k, int *flag)
+{
+    bool bad = false;
+    const size_t cells = (size_t)W * H;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(c / W), x = (int)(c % W);
+        T g[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + 1) * pitch + x];
+        const Moments<T> m = moments(g);
+        const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));
+        bad |= equilibrium_i(0, m.rho, m.vx, m.vy, v2, k) < T(0);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+mask_any_kernel(const uint8_t *mask, int mask_pitch, int W, int H, int *flag)
+{
+    bool any = false;
+    const size_t cells = (size_t)W * H;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(c / W), x = (int)(c % W);
+        any |= mask[(size_t)y * mask_pitch + x] != 0;
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+inline int check_launch()
+{
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+inline int reduction_blocks(size_t cells)
+{
+    size_t b = (cells + RED_THREADS - 1) / RED_THREADS;
+    if (b > (size_t)RED_MAX_BLOCKS) b = RED_MAX_BLOCKS;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename T>
+bool use_vec(const StepArgs<T> &a) { return a.W % VecOf<T>::N == 0; }
+
+}  // namespace
+
+template <typename T>
+const char *step_kernel_name(const StepArgs<T> &a)
+{
+    if (!use_vec(a)) return sizeof(T) == 4 ? "step_scalar_kernel<float>" : "step_scalar_kernel<double>";
+    return sizeof(T) == 4 ? "step_vec_kernel<float>" : "step_vec_kernel<double>";
+}
+
+template <typename T>
+int launch_step(const StepArgs<T> &a, cudaStream_t s)
+{
+    const int rows = a.y_end - a.y_begin;
+    if (rows <= 0) return 0;
+    if (use_vec(a)) {
+        constexpr int V = VecOf<T>::N;
+        const int nvec = a.W / V;
+        int bx = ((nvec + 31) / 32) * 32;
+        if (bx > STEP_THREADS) bx = STEP_THREADS;
+        int by = STEP_THREADS / bx;
+        if (by > rows) by = rows;
+        const dim3 block(bx, by);
+        const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
+        if (a.periodic_x) {
+            if (a.has_mask) step_vec_kernel<T, true, true><<<grid, block, 0, s>>>(a);
+            else            step_vec_kernel<T, true, false><<<grid, block, 0, s>>>(a);
+        } else {
+            if (a.has_mask) step_vec_kernel<T, false, true><<<grid, block, 0, s>>>(a);
+            else            step_vec_kernel<T, false, false><<<grid, block, 0, s>>>(a);
+        }
+    } else {
+        int bx = ((a.W + 31) / 32) * 32;
+        if (bx > STEP_THREADS) bx = STEP_THREADS;
+        int by = STEP_THREADS / bx;
+        if (by > rows) by = rows;
+        const dim3 block(bx, by);
+        const dim3 grid((rows + by - 1) / by, (a.W + bx - 1) / bx);
+        step_scalar_kernel<T><<<grid, block, 0, s>>>(a);
+    }
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+template <typename T>
+int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane, int pitch, int W, int H,
+                            const Consts<T> &k, cudaStream_t s)
+{
+    const dim3 block(256), grid(H, (W + 255) / 256);
+    init_equilibrium_kernel<T><<<grid, block, 0, s>>>(rho, vx, vy, dst, plane, pitch, W, H, k);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+template <typename T>
+int launch_readout(const ReadoutArgs<T> &a, cudaStream_t s)
+{
+    const dim3 block(256), grid(a.H, (a.W + 255) / 256);
+    readout_kernel<T><<<grid, block, 0, s>>>(a);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+int mass_partials_capacity() { return RED_MAX_BLOCKS; }
+
+template <typename T>
+int launch_total_mass(const T *src, size_t plane, int pitch, int W, int H, double *partials, double *out,
+                      cudaStream_t s)
+{
+    const int blocks = reduction_blocks((size_t)W * H);
+    mass_partial_kernel<T><<<blocks, RED_THREADS, 0, s>>>(src, plane, pitch, W, H, partials);
+    mass_final_kernel<<<1, RED_THREADS, 0, s>>>(partials, blocks, out);
+    const int e = check_launch();
+    return e ? e : 2;
+}
+
+template <typename T>
+int launch_is_unstable(const T *src, size_t plane, int pitch, int W, int H, const Consts<T> &k, int *flag,
+                       cudaStream_t s)
+{
+    const int blocks = reduction_blocks((size_t)W * H);
+    unstable_kernel<T><<<blocks, RED_THREADS, 0, s>>>(src, plane, pitch, W, H, k, flag);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+int launch_mask_any(const uint8_t *mask, int mask_pitch, int W, int H, int *flag, cudaStream_t s)
+{
+    const int blocks = reduction_blocks((size_t)W * H);
+    mask_any_kernel<<<blocks, RED_THREADS, 0, s>>>(mask, mask_pitch, W, H, flag);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+#define CHEMSIM_INSTANTIATE(T)                                                                                       \
+    template int launch_step<T>(const StepArgs<T> &, cudaStream_t);                                                  \
+    template const char *step_kernel_name<T>(const StepArgs<T> &);                                                   \
+    template int launch_init_equilibrium<T>(const T *, const T *, const T *, T *, size_t, int, int, int,             \
+                                            const Consts<T> &, cudaStream_t);                                        \
+    template int launch_readout<T>(const ReadoutArgs<T> &, cudaStream_t);                                            \
+    template int launch_total_mass<T>(const T *, size_t, int, int, int, double *, double *, cudaStream_t);           \
+    template int launch_is_unstable<T>(const T *, size_t, int, int, int, const Consts<T> &, int *, cudaStream_t);
+
+CHEMSIM_INSTANTIATE(float)
+CHEMSIM_INSTANTIATE(double)
+
+}  // namespace chemsim

@@ -1,0 +1,62 @@
+// kernels.cuh — launch interface between the host runtime (lattice.cu) and the
+// sm_100a kernels (kernels.cu).
+#pragma once
+
+#include "d2q9.cuh"
+
+namespace chemsim {
+
+// Device layout of one population set ("lattice buffer"):
+//   value of population q at local row y (−1 … H, the two extremes being ghost
+//   rows) and column x lives at  base[q*plane + (y+1)*pitch + x].
+// pitch is W rounded up to 128 bytes so every row starts on a cache line and
+// 128-bit vector accesses at x % VEC == 0 are aligned.
+template <typename T>
+struct StepArgs {
+    const T *src;
+    T *dst;
+    size_t plane;          // elements per population plane = (H+2)*pitch
+    int pitch;             // elements per row
+    int W, H;              // local lattice: W columns, H rows
+    int y_begin, y_end;    // rows updated by this launch
+    int wrap_y;            // 1: rows −1/H alias rows H−1/0 (periodic, unsharded); 0: read the ghost rows
+    int periodic_x;        // 1: wrap in x; 0: zero-fill (reference)
+    const uint8_t *mask;   // H rows of mask_pitch bytes, non-zero = solid
+    int mask_pitch;
+    int has_mask;          // 0: no solid cell anywhere in this slab, mask not read
+    Consts<T> k;
+};
+
+enum ReadoutKind : int {
+    READ_DENSITY = 0, READ_PRESSURE, READ_SPEED, READ_VELOCITY, READ_MOMENTUM,
+    READ_EQUILIBRIUM, READ_NON_EQUILIBRIUM
+};
+
+template <typename T>
+struct ReadoutArgs {
+    const T *src;
+    size_t plane;
+    int pitch;
+    int W, H;
+    int kind;
+    int q;          // for READ_EQUILIBRIUM / READ_NON_EQUILIBRIUM
+    T *out0, *out1; // dense (pitch == W) outputs
+    Consts<T> k;
+};
+
+// Each launcher returns the number of kernels it launched (for the handle's
+// launch counter) or a negative cudaError_t.
+template <typename T> int launch_step(const StepArgs<T> &a, cudaStream_t s);
+template <typename T> const char *step_kernel_name(const StepArgs<T> &a);
+template <typename T> int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane,
+                                                  int pitch, int W, int H, const Consts<T> &k, cudaStream_t s);
+template <typename T> int launch_readout(const ReadoutArgs<T> &a, cudaStream_t s);
+// partials: at least mass_partials_capacity() doubles; out: one double
+int mass_partials_capacity();
+template <typename T> int launch_total_mass(const T *src, size_t plane, int pitch, int W, int H, double *partials,
+                                            double *out, cudaStream_t s);
+template <typename T> int launch_is_unstable(const T *src, size_t plane, int pitch, int W, int H, const Consts<T> &k,
+                                             int *flag, cudaStream_t s);
+int launch_mask_any(const uint8_t *mask, int mask_pitch, int W, int H, int *flag, cudaStream_t s);
+
+}  // namespace chemsim

@@ -1,0 +1,684 @@
+// lattice.cu — host runtime behind the C ABI of include/chemsim_lbm.h.
+//
+// Owns the device-resident State (two population buffers for A-B stepping, the
+// geometry mask, staging for readouts), the compute and halo streams and, for a
+// sharded lattice, the NCCL communicator.  No CPU fallback: every compute entry
+// point needs a CUDA device.
+#include "../../include/chemsim_lbm.h"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace chemsim;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+struct Scalars {   // host scalars in both dtypes, rebuilt whenever dx/dt/tau change
+    Consts<float> f;
+    Consts<double> d;
+};
+
+template <typename T>
+Consts<T> make_consts(double dx_, double dt_, double tau_)
+{
+    Consts<T> k;
+    static const int num[Q] = {16, 4, 4, 4, 4, 1, 1, 1, 1};
+    for (int i = 0; i < Q; ++i) k.w[i] = (T)num[i] / (T)36.0;            // src/lbm.rs:209-219
+    const T dx = (T)dx_, dt = (T)dt_;
+    const T cs = dx / (std::sqrt((T)3.0) * dt);                           // src/lbm.rs:84
+    k.cs2 = cs * cs;                                                      // :55
+    const T cs4 = k.cs2 * k.cs2;                                          // :56
+    k.k1 = (T)1.0 / k.cs2;                                                // :64
+    k.k2 = (T)1.0 / ((T)2.0 * cs4);                                       // :65
+    k.k3 = (T)-1.0 / ((T)2.0 * k.cs2);                                    // :66
+    k.factor = tau_ != 0.0 ? -dt / (T)tau_ : (T)0;                        // :357
+    return k;
+}
+
+}  // namespace
+
+struct chemsim_lbm {
+    int W = 0, H = 0, Hglobal = 0, row0 = 0;
+    int dtype = 0, edge = 0, device = 0;
+    int rank = 0, nranks = 1;
+    size_t esize = 4;
+    double dx = 1.0, dt = 1.0, tau = 0.0;
+    int collision = CHEMSIM_LBM_COLLISION_NONE;
+    Scalars k;
+
+    void *buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t plane = 0;   // elements
+    int pitch = 0;      // elements
+    uint8_t *mask = nullptr;
+    int mask_pitch = 0;
+    int has_mask = 0;
+    void *stage[3] = {nullptr, nullptr, nullptr};   // dense W*H fields
+    double *d_partials = nullptr, *d_scalar = nullptr;
+    int *d_flag = nullptr;
+    double *h_scalar = nullptr;   // pinned
+    int *h_flag = nullptr;        // pinned
+
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_exchange = nullptr;
+    ncclComm_t comm = nullptr;
+    bool ghosts_valid = false;
+    bool have_populations = false;
+
+    float time_f = 0.f;
+    double time_d = 0.0;
+    uint64_t launches = 0;
+    std::string err = "";
+};
+
+namespace {
+
+int fail(chemsim_lbm *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        const cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, CHEMSIM_LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define NCCL_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        const ncclResult_t r_ = (expr);                                                        \
+        if (r_ != ncclSuccess)                                                                 \
+            return fail(h, CHEMSIM_LBM_ERR_NCCL, std::string(#expr) + ": " + nccl_dyn().GetErrorString(r_)); \
+    } while (0)
+
+#define LAUNCH_TRY(h, expr)                                                                    \
+    do {                                                                                       \
+        const int n_ = (expr);                                                                 \
+        if (n_ < 0)                                                                            \
+            return fail(h, CHEMSIM_LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)(-n_))); \
+        (h)->launches += (uint64_t)n_;                                                         \
+    } while (0)
+
+int bind_device(chemsim_lbm *h) { CUDA_TRY(h, cudaSetDevice(h->device)); return 0; }
+
+#define BIND(h) do { const int b_ = bind_device(h); if (b_) return b_; } while (0)
+
+int check_n(chemsim_lbm *h, size_t n)
+{
+    if (n != (size_t)h->W * (size_t)h->H)
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE,
+                    "slice has " + std::to_string(n) + " elements, lattice slab is " + std::to_string(h->W) + "x" +
+                        std::to_string(h->H));
+    return 0;
+}
+
+void rebuild_scalars(chemsim_lbm *h)
+{
+    h->k.f = make_consts<float>(h->dx, h->dt, h->tau);
+    h->k.d = make_consts<double>(h->dx, h->dt, h->tau);
+}
+
+char *row_ptr(chemsim_lbm *h, int b, int q, int y)
+{
+    return (char *)h->buf[b] + ((size_t)q * h->plane + (size_t)(y + 1) * h->pitch) * h->esize;
+}
+
+template <typename T> const Consts<T> &consts_of(const chemsim_lbm *h);
+template <> const Consts<float> &consts_of<float>(const chemsim_lbm *h) { return h->k.f; }
+template <> const Consts<double> &consts_of<double>(const chemsim_lbm *h) { return h->k.d; }
+
+template <typename T>
+StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_end)
+{
+    StepArgs<T> a;
+    a.src = (const T *)h->buf[h->cur];
+    a.dst = (T *)h->buf[h->cur ^ 1];
+    a.plane = h->plane;
+    a.pitch = h->pitch;
+    a.W = h->W;
+    a.H = h->H;
+    a.y_begin = y_begin;
+    a.y_end = y_end;
+    a.wrap_y = (h->edge == CHEMSIM_LBM_EDGE_PERIODIC && h->nranks == 1) ? 1 : 0;
+    a.periodic_x = h->edge == CHEMSIM_LBM_EDGE_PERIODIC ? 1 : 0;
+    a.mask = h->mask;
+    a.mask_pitch = h->mask_pitch;
+    a.has_mask = h->has_mask;
+    a.k = consts_of<T>(h);
+    return a;
+}
+
+// Halo exchange of buffer b: populations moving towards larger y
+// (dy=+1: q = 3,6,7) go from my last row to the lower neighbour's ghost row −1;
+// populations moving towards smaller y (dy=−1: q = 1,5,8) go from my first row to
+// the upper neighbour's ghost row H.  Rows of one population are contiguous, so
+// the sends/receives work directly on the lattice buffers (no packing).
+int exchange(chemsim_lbm *h, int b)
+{
+    const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
+    const int up = (h->rank + h->nranks - 1) % h->nranks, down = (h->rank + 1) % h->nranks;
+    const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
+    const size_t bytes = (size_t)h->W * h->esize;
+    static const int to_down[3] = {3, 6, 7}, to_up[3] = {1, 5, 8};
+    const NcclDyn &n = nccl_dyn();
+    NCCL_TRY(h, n.GroupStart());
+    if (has_down) for (int q : to_down) NCCL_TRY(h, n.Send(row_ptr(h, b, q, h->H - 1), bytes, ncclChar, down, h->comm, h->comm_stream));
+    if (has_up)   for (int q : to_up)   NCCL_TRY(h, n.Send(row_ptr(h, b, q, 0), bytes, ncclChar, up, h->comm, h->comm_stream));
+    if (has_up)   for (int q : to_down) NCCL_TRY(h, n.Recv(row_ptr(h, b, q, -1), bytes, ncclChar, up, h->comm, h->comm_stream));
+    if (has_down) for (int q : to_up)   NCCL_TRY(h, n.Recv(row_ptr(h, b, q, h->H), bytes, ncclChar, down, h->comm, h->comm_stream));
+    NCCL_TRY(h, n.GroupEnd());
+    h->launches += 1;   // one fused NCCL send/recv kernel per group
+    return 0;
+}
+
+// Make the ghost rows of the current buffer valid (after an upload).
+int ensure_ghosts(chemsim_lbm *h)
+{
+    if (h->nranks == 1 || h->ghosts_valid) return 0;
+    CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+    const int r = exchange(h, h->cur);
+    if (r) return r;
+    CUDA_TRY(h, cudaEventRecord(h->ev_exchange, h->comm_stream));
+    h->ghosts_valid = true;
+    return 0;
+}
+
+template <typename T>
+int step_impl(chemsim_lbm *h, int nsteps)
+{
+    if (h->nranks == 1) {
+        for (int s = 0; s < nsteps; ++s) {
+            LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H), h->stream));
+            h->cur ^= 1;
+        }
+        return 0;
+    }
+    const int r0 = ensure_ghosts(h);
+    if (r0) return r0;
+    for (int s = 0; s < nsteps; ++s) {
+        // 1. the two face rows need the ghost rows of `cur`: wait for its exchange
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_exchange, 0));
+        LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, 1), h->stream));
+        if (h->H > 1) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, h->H - 1, h->H), h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));
+        // 2. ship the new face rows on the side stream ...
+        CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+        const int r = exchange(h, h->cur ^ 1);
+        if (r) return r;
+        CUDA_TRY(h, cudaEventRecord(h->ev_exchange, h->comm_stream));
+        // 3. ... while the interior (which reads no ghost row) is updated
+        if (h->H > 2) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 1, h->H - 1), h->stream));
+        h->cur ^= 1;
+    }
+    return 0;
+}
+
+int upload_field(chemsim_lbm *h, void *dst_dense, const void *src)
+{
+    CUDA_TRY(h, cudaMemcpyAsync(dst_dense, src, (size_t)h->W * h->H * h->esize, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int ensure_stage(chemsim_lbm *h, int count)
+{
+    for (int i = 0; i < count; ++i)
+        if (!h->stage[i]) CUDA_TRY(h, cudaMalloc(&h->stage[i], (size_t)h->W * h->H * h->esize));
+    return 0;
+}
+
+template <typename T>
+int readout_impl(chemsim_lbm *h, int kind, int q, void *dst0, void *dst1)
+{
+    const int rs = ensure_stage(h, dst1 ? 2 : 1);
+    if (rs) return rs;
+    ReadoutArgs<T> a;
+    a.src = (const T *)h->buf[h->cur];
+    a.plane = h->plane; a.pitch = h->pitch; a.W = h->W; a.H = h->H;
+    a.kind = kind; a.q = q;
+    a.out0 = (T *)h->stage[0]; a.out1 = (T *)h->stage[1];
+    a.k = consts_of<T>(h);
+    LAUNCH_TRY(h, launch_readout<T>(a, h->stream));
+    const size_t bytes = (size_t)h->W * h->H * sizeof(T);
+    CUDA_TRY(h, cudaMemcpyAsync(dst0, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (dst1) CUDA_TRY(h, cudaMemcpyAsync(dst1, h->stage[1], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int readout(chemsim_lbm *h, int kind, int q, void *dst0, void *dst1, size_t n)
+{
+    if (!h || !dst0) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    return h->dtype == CHEMSIM_LBM_F32 ? readout_impl<float>(h, kind, q, dst0, dst1)
+                                       : readout_impl<double>(h, kind, q, dst0, dst1);
+}
+
+int local_mass(chemsim_lbm *h)   // result left in h->d_scalar
+{
+    if (h->dtype == CHEMSIM_LBM_F32)
+        LAUNCH_TRY(h, launch_total_mass<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H,
+                                               h->d_partials, h->d_scalar, h->stream));
+    else
+        LAUNCH_TRY(h, launch_total_mass<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H,
+                                                h->d_partials, h->d_scalar, h->stream));
+    return 0;
+}
+
+int create_impl(int width, int global_height, int dtype, int edge, int device, int rank, int nranks,
+                const void *nccl_id, chemsim_lbm_t **out)
+{
+    if (!out) return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (width <= 0 || global_height <= 0)
+        return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "width and height must be positive");
+    if (dtype != CHEMSIM_LBM_F32 && dtype != CHEMSIM_LBM_F64)
+        return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "dtype must be CHEMSIM_LBM_F32 or CHEMSIM_LBM_F64");
+    if (edge != CHEMSIM_LBM_EDGE_ZEROFILL && edge != CHEMSIM_LBM_EDGE_PERIODIC)
+        return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "edge must be ZEROFILL or PERIODIC");
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "need 0 <= rank < nranks");
+    if (nranks > 1 && !nccl_id) return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "nccl_id is null");
+    if (global_height < nranks)
+        return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "fewer rows than ranks");
+
+    if (device < 0) {
+        const cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return fail(nullptr, CHEMSIM_LBM_ERR_CUDA, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+    }
+    chemsim_lbm *h = new (std::nothrow) chemsim_lbm;
+    if (!h) return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "out of host memory");
+    h->W = width;
+    h->Hglobal = global_height;
+    h->row0 = (int)(((long long)global_height * rank) / nranks);
+    h->H = (int)(((long long)global_height * (rank + 1)) / nranks) - h->row0;
+    h->dtype = dtype; h->edge = edge; h->device = device; h->rank = rank; h->nranks = nranks;
+    h->esize = dtype == CHEMSIM_LBM_F32 ? 4 : 8;
+    const int per_line = (int)(128 / h->esize);
+    h->pitch = ((width + per_line - 1) / per_line) * per_line;
+    h->plane = (size_t)(h->H + 2) * h->pitch;
+    h->mask_pitch = ((width + 127) / 128) * 128;
+    rebuild_scalars(h);
+
+#define CREATE_TRY(expr)                                                                        \
+    do {                                                                                        \
+        const cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess) {                                                                \
+            const int rc_ = fail(nullptr, CHEMSIM_LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+            chemsim_lbm_destroy(h);                                                             \
+            return rc_;                                                                         \
+        }                                                                                       \
+    } while (0)
+
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_exchange, cudaEventDisableTiming));
+    const size_t buf_bytes = (size_t)Q * h->plane * h->esize;
+    for (int b = 0; b < 2; ++b) {
+        CREATE_TRY(cudaMalloc(&h->buf[b], buf_bytes));
+        CREATE_TRY(cudaMemsetAsync(h->buf[b], 0, buf_bytes, h->stream));   // ghost rows of a zero-fill edge stay 0
+    }
+    CREATE_TRY(cudaMalloc((void **)&h->mask, (size_t)h->H * h->mask_pitch));
+    CREATE_TRY(cudaMemsetAsync(h->mask, 0, (size_t)h->H * h->mask_pitch, h->stream));
+    CREATE_TRY(cudaMalloc((void **)&h->d_partials, sizeof(double) * mass_partials_capacity()));
+    CREATE_TRY(cudaMalloc((void **)&h->d_scalar, 2 * sizeof(double)));
+    CREATE_TRY(cudaMalloc((void **)&h->d_flag, sizeof(int)));
+    CREATE_TRY(cudaMallocHost((void **)&h->h_scalar, 2 * sizeof(double)));
+    CREATE_TRY(cudaMallocHost((void **)&h->h_flag, sizeof(int)));
+    CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+
+    if (nranks > 1) {
+        const NcclDyn &n = nccl_dyn();
+        if (!n.ok) {
+            const int rc = fail(nullptr, CHEMSIM_LBM_ERR_NCCL, "libnccl.so.2 could not be loaded: " + n.error);
+            chemsim_lbm_destroy(h);
+            return rc;
+        }
+        ncclUniqueId id;
+        static_assert(sizeof(id) == CHEMSIM_LBM_NCCL_ID_BYTES, "ncclUniqueId size");
+        std::memcpy(&id, nccl_id, sizeof(id));
+        const ncclResult_t r = n.CommInitRank(&h->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            const int rc = fail(nullptr, CHEMSIM_LBM_ERR_NCCL, std::string("ncclCommInitRank: ") + n.GetErrorString(r));
+            chemsim_lbm_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return CHEMSIM_LBM_OK;
+}
+
+}  // namespace
+
+// =============================== C ABI ========================================
+
+extern "C" {
+
+int chemsim_lbm_abi_version(void) { return CHEMSIM_LBM_ABI_VERSION; }
+
+const char *chemsim_lbm_last_error(const chemsim_lbm_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int chemsim_lbm_create(int width, int height, int dtype, int edge, int device, chemsim_lbm_t **out)
+{
+    return create_impl(width, height, dtype, edge, device, 0, 1, nullptr, out);
+}
+
+int chemsim_lbm_create_slab(int width, int global_height, int dtype, int edge, int device, int rank, int nranks,
+                            const void *nccl_id, chemsim_lbm_t **out)
+{
+    return create_impl(width, global_height, dtype, edge, device, rank, nranks, nccl_id, out);
+}
+
+int chemsim_lbm_nccl_unique_id(void *out_id)
+{
+    if (!out_id) return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "out_id is null");
+    const NcclDyn &n = nccl_dyn();
+    if (!n.ok) return fail(nullptr, CHEMSIM_LBM_ERR_NCCL, "libnccl.so.2 could not be loaded: " + n.error);
+    ncclUniqueId id;
+    const ncclResult_t r = n.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, CHEMSIM_LBM_ERR_NCCL, std::string("ncclGetUniqueId: ") + n.GetErrorString(r));
+    std::memcpy(out_id, &id, sizeof(id));
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_destroy(chemsim_lbm_t *h)
+{
+    if (!h) return CHEMSIM_LBM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    if (h->comm) nccl_dyn().CommDestroy(h->comm);
+    for (int b = 0; b < 2; ++b) if (h->buf[b]) cudaFree(h->buf[b]);
+    for (int i = 0; i < 3; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->mask) cudaFree(h->mask);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_scalar) cudaFree(h->d_scalar);
+    if (h->d_flag) cudaFree(h->d_flag);
+    if (h->h_scalar) cudaFreeHost(h->h_scalar);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
+    if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
+    if (h->ev_exchange) cudaEventDestroy(h->ev_exchange);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    delete h;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_shape(const chemsim_lbm_t *h, int *width, int *local_height, int *global_height, int *row_offset)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (width) *width = h->W;
+    if (local_height) *local_height = h->H;
+    if (global_height) *global_height = h->Hglobal;
+    if (row_offset) *row_offset = h->row0;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_discretization(chemsim_lbm_t *h, double delta_x, double delta_t)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (!(delta_x > 0.0) || !(delta_t > 0.0)) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "delta_x and delta_t must be positive");
+    h->dx = delta_x; h->dt = delta_t;
+    rebuild_scalars(h);
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_bgk(chemsim_lbm_t *h, double tau)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (tau == 0.0 || tau != tau) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "tau must be a non-zero number");
+    h->tau = tau;
+    h->collision = CHEMSIM_LBM_COLLISION_BGK;
+    rebuild_scalars(h);
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_kinematic_shear_viscosity(const chemsim_lbm_t *h, double *out)
+{
+    if (!h || !out) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (h->collision != CHEMSIM_LBM_COLLISION_BGK) return CHEMSIM_LBM_ERR_NOT_READY;
+    if (h->dtype == CHEMSIM_LBM_F32) {   // src/lbm.rs:366-369
+        const float dx = (float)h->dx, dt = (float)h->dt, tau = (float)h->tau;
+        *out = (double)((dx * dx / (3.0f * dt * dt)) * (tau - dt / 2.0f));
+    } else {
+        const double dx = h->dx, dt = h->dt, tau = h->tau;
+        *out = (dx * dx / (3.0 * dt * dt)) * (tau - dt / 2.0);
+    }
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_kinematic_bulk_viscosity(const chemsim_lbm_t *h, double *out)
+{
+    double nu = 0.0;
+    const int r = chemsim_lbm_kinematic_shear_viscosity(h, &nu);
+    if (r) return r;
+    if (h->dtype == CHEMSIM_LBM_F32) *out = (double)(2.0f * (float)nu / 3.0f);   // src/lbm.rs:338-340
+    else *out = 2.0 * nu / 3.0;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_init_equilibrium(chemsim_lbm_t *h, const void *rho, const void *vx, const void *vy, size_t n)
+{
+    if (!h || !rho || !vx || !vy) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    const int rs = ensure_stage(h, 3);
+    if (rs) return rs;
+    int r;
+    if ((r = upload_field(h, h->stage[0], rho)) || (r = upload_field(h, h->stage[1], vx)) ||
+        (r = upload_field(h, h->stage[2], vy)))
+        return r;
+    if (h->dtype == CHEMSIM_LBM_F32)
+        LAUNCH_TRY(h, launch_init_equilibrium<float>((const float *)h->stage[0], (const float *)h->stage[1],
+                                                     (const float *)h->stage[2], (float *)h->buf[h->cur], h->plane,
+                                                     h->pitch, h->W, h->H, h->k.f, h->stream));
+    else
+        LAUNCH_TRY(h, launch_init_equilibrium<double>((const double *)h->stage[0], (const double *)h->stage[1],
+                                                      (const double *)h->stage[2], (double *)h->buf[h->cur], h->plane,
+                                                      h->pitch, h->W, h->H, h->k.d, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // the host buffers may be pageable / reused by the caller
+    h->have_populations = true;
+    h->ghosts_valid = false;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_population(chemsim_lbm_t *h, int q, const void *src, size_t n)
+{
+    if (!h || !src) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (q < 0 || q >= Q) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "q must be in 0..9");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    CUDA_TRY(h, cudaMemcpy2DAsync(row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize, src, (size_t)h->W * h->esize,
+                                  (size_t)h->W * h->esize, h->H, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_populations = true;
+    h->ghosts_valid = false;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_geometry(chemsim_lbm_t *h, const uint8_t *solid, size_t n)
+{
+    if (!h || !solid) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->mask, h->mask_pitch, solid, h->W, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    LAUNCH_TRY(h, launch_mask_any(h->mask, h->mask_pitch, h->W, h->H, h->d_flag, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->has_mask = *h->h_flag ? 1 : 0;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_step(chemsim_lbm_t *h, int nsteps)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (nsteps < 0) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "nsteps must be >= 0");
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set (init_equilibrium / set_population)");
+    if (h->collision == CHEMSIM_LBM_COLLISION_NONE) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "collision operator not set (set_bgk)");
+    BIND(h);
+    const int r = h->dtype == CHEMSIM_LBM_F32 ? step_impl<float>(h, nsteps) : step_impl<double>(h, nsteps);
+    if (r) return r;
+    for (int s = 0; s < nsteps; ++s) {   // self.time += delta_t, in Scalar (src/lbm.rs:713)
+        h->time_f += (float)h->dt;
+        h->time_d += h->dt;
+    }
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_synchronize(chemsim_lbm_t *h)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    BIND(h);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_time(const chemsim_lbm_t *h, double *out)
+{
+    if (!h || !out) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *out = h->dtype == CHEMSIM_LBM_F32 ? (double)h->time_f : h->time_d;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_get_density(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_DENSITY, 0, dst, nullptr, n); }
+int chemsim_lbm_get_pressure(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_PRESSURE, 0, dst, nullptr, n); }
+int chemsim_lbm_get_speed(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_SPEED, 0, dst, nullptr, n); }
+
+int chemsim_lbm_get_velocity(chemsim_lbm_t *h, void *vx, void *vy, size_t n)
+{
+    if (!vy) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    return readout(h, READ_VELOCITY, 0, vx, vy, n);
+}
+
+int chemsim_lbm_get_momentum_density(chemsim_lbm_t *h, void *mx, void *my, size_t n)
+{
+    if (!my) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    return readout(h, READ_MOMENTUM, 0, mx, my, n);
+}
+
+int chemsim_lbm_get_population(chemsim_lbm_t *h, int q, void *dst, size_t n)
+{
+    if (!h || !dst) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (q < 0 || q >= Q) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "q must be in 0..9");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    CUDA_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->W * h->esize, row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize,
+                                  (size_t)h->W * h->esize, h->H, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_get_equilibrium(chemsim_lbm_t *h, int q, void *dst, size_t n)
+{
+    if (q < 0 || q >= Q) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "q must be in 0..9");
+    return readout(h, READ_EQUILIBRIUM, q, dst, nullptr, n);
+}
+
+int chemsim_lbm_get_non_equilibrium(chemsim_lbm_t *h, int q, void *dst, size_t n)
+{
+    if (q < 0 || q >= Q) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "q must be in 0..9");
+    return readout(h, READ_NON_EQUILIBRIUM, q, dst, nullptr, n);
+}
+
+int chemsim_lbm_get_geometry(chemsim_lbm_t *h, uint8_t *dst, size_t n)
+{
+    if (!h || !dst) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    CUDA_TRY(h, cudaMemcpy2DAsync(dst, h->W, h->mask, h->mask_pitch, h->W, h->H, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_total_mass(chemsim_lbm_t *h, double *out)
+{
+    if (!h || !out) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    BIND(h);
+    const int r = local_mass(h);
+    if (r) return r;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_scalar, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *out = h->h_scalar[0];
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_total_mass_global(chemsim_lbm_t *h, double *out)
+{
+    if (!h || !out) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (h->nranks == 1) return chemsim_lbm_total_mass(h, out);
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    BIND(h);
+    const int r = local_mass(h);
+    if (r) return r;
+    NCCL_TRY(h, nccl_dyn().AllReduce(h->d_scalar, h->d_scalar + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    h->launches += 1;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_scalar, h->d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *out = h->h_scalar[0];
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_is_unstable(chemsim_lbm_t *h, int *out)
+{
+    if (!h || !out) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    BIND(h);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    if (h->dtype == CHEMSIM_LBM_F32)
+        LAUNCH_TRY(h, launch_is_unstable<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, h->k.f,
+                                                h->d_flag, h->stream));
+    else
+        LAUNCH_TRY(h, launch_is_unstable<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, h->k.d,
+                                                 h->d_flag, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *out = *h->h_flag ? 1 : 0;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_cuda_stream(const chemsim_lbm_t *h, void **stream)
+{
+    if (!h || !stream) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *stream = (void *)h->stream;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_kernel_launches(const chemsim_lbm_t *h, uint64_t *out)
+{
+    if (!h || !out) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *out = h->launches;
+    return CHEMSIM_LBM_OK;
+}
+
+const char *chemsim_lbm_step_kernel_name(const chemsim_lbm_t *h)
+{
+    if (!h) return "";
+    return h->dtype == CHEMSIM_LBM_F32 ? step_kernel_name<float>(step_args<float>(h, 0, h->H))
+                                       : step_kernel_name<double>(step_args<double>(h, 0, h->H));
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+/*
+ * chemsim_lbm.h — C ABI of the B200-native D2Q9 collide+stream path.
+ *
+ * This is the drop-in boundary for the hot path of taktoa/chemsim's
+ * src/lbm.rs: every entry point below is what an FFI binding of lbm.rs would
+ * bind, and each cites the reference item (file:line, relative to the
+ * reference tree) it replaces.  The reference has no FFI of its own — its
+ * boundary is the set of lbm.rs / matrix.rs items that main.rs, render.rs and
+ * display.rs touch — so the Rust shim that keeps those names
+ * on top of this ABI is given in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Host fields are row-major, element (y,x)
+ *    at [y*w + x], exactly what Matrix::new takes and Matrix::get_underlying
+ *    returns (src/matrix.rs:24-30, :120-126).  `n` arguments are element
+ *    counts and must equal width*local_height, else
+ *    CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE (= matrix::Error::InvalidSliceSize,
+ *    src/matrix.rs:15-19, :26).
+ *  - Element type of every `void*` field is the lattice dtype given at create
+ *    time (float for F32 — the reference's `Scalar`, src/lbm.rs:13 — or double).
+ *  - Every function returns 0 on success or a chemsim_lbm_status; the message
+ *    is available from chemsim_lbm_last_error().  Nothing unwinds or aborts
+ *    across the boundary (the reference panics/aborts, Cargo.toml:128; the Rust
+ *    shim maps non-zero statuses back to those panics / Results).
+ *  - One caller thread per handle (the reference is single-threaded,
+ *    src/display.rs:121-147).  All work is queued on the handle's CUDA stream;
+ *    functions that return host data synchronise that stream, the others are
+ *    asynchronous and ordered with later calls.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with CHEMSIM_LBM_ERR_CUDA.
+ */
+#ifndef CHEMSIM_LBM_H
+#define CHEMSIM_LBM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHEMSIM_LBM_ABI_VERSION 1
+#define CHEMSIM_LBM_Q 9
+#define CHEMSIM_LBM_NCCL_ID_BYTES 128
+
+typedef struct chemsim_lbm chemsim_lbm_t; /* opaque; owns all device memory */
+
+typedef enum {
+    CHEMSIM_LBM_F32 = 0, /* reference: `pub type Scalar = f32`, src/lbm.rs:13 */
+    CHEMSIM_LBM_F64 = 1  /* extension: same operation order evaluated in f64  */
+} chemsim_lbm_dtype;
+
+typedef enum {
+    CHEMSIM_LBM_EDGE_ZEROFILL = 0, /* reference: af::convolve2 zero padding, src/lbm.rs:722-724 */
+    CHEMSIM_LBM_EDGE_PERIODIC = 1  /* extension: wrap-around (BASELINE.json configs 2,4,5)      */
+} chemsim_lbm_edge;
+
+typedef enum {
+    CHEMSIM_LBM_OK = 0,
+    CHEMSIM_LBM_ERR_INVALID_ARGUMENT = 1,
+    CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE = 2, /* matrix::Error::InvalidSliceSize */
+    CHEMSIM_LBM_ERR_CUDA = 3,
+    CHEMSIM_LBM_ERR_NCCL = 4,
+    CHEMSIM_LBM_ERR_NOT_READY = 5, /* step before populations / collision were set */
+    CHEMSIM_LBM_ERR_UNSUPPORTED = 6
+} chemsim_lbm_status;
+
+typedef enum {                     /* CollisionOperator impls, src/lbm.rs:327-666 */
+    CHEMSIM_LBM_COLLISION_NONE = 0,
+    CHEMSIM_LBM_COLLISION_BGK = 1  /* src/lbm.rs:345-370 */
+} chemsim_lbm_collision;
+
+/* ---- library -------------------------------------------------------------- */
+
+int chemsim_lbm_abi_version(void);
+/* Message of the last failure on `h` (or, with h == NULL, of the last failed
+ * create on this thread).  Never NULL. */
+const char *chemsim_lbm_last_error(const chemsim_lbm_t *h);
+
+/* ---- construction / ownership --------------------------------------------- */
+
+/* One lattice on one GPU.  Replaces D2Q9::new + State::initial
+ * (src/lbm.rs:187-200, :679-692): the handle is the device-resident State.
+ * `device` < 0 keeps the current CUDA device. */
+int chemsim_lbm_create(int width, int height, int dtype, int edge, int device, chemsim_lbm_t **out);
+
+/* One y-slab of a lattice sharded over `nranks` processes (one per GPU): rank r
+ * owns global rows [r*H/nranks, (r+1)*H/nranks).  Neighbouring slabs exchange
+ * one row of three populations per face per step with ncclSend/ncclRecv on a
+ * side stream, overlapped with the interior update.  `nccl_id` is the 128-byte
+ * id from chemsim_lbm_nccl_unique_id() on rank 0, distributed by the caller
+ * (e.g. torch.distributed / MPI broadcast).  New functionality: the reference is
+ * single-device. */
+int chemsim_lbm_create_slab(int width, int global_height, int dtype, int edge, int device, int rank,
+                            int nranks, const void *nccl_id, chemsim_lbm_t **out);
+int chemsim_lbm_nccl_unique_id(void *out_id /* CHEMSIM_LBM_NCCL_ID_BYTES */);
+
+int chemsim_lbm_destroy(chemsim_lbm_t *h); /* Drop for State */
+
+/* State::size (src/lbm.rs:753-756) and the slab this handle owns. */
+int chemsim_lbm_shape(const chemsim_lbm_t *h, int *width, int *local_height, int *global_height,
+                      int *row_offset);
+
+/* ---- parameters ----------------------------------------------------------- */
+
+/* Discretization{delta_x, delta_t} (src/lbm.rs:75-86).  Default 1, 1.  The host
+ * scalars cs^2, 1/cs^2, 1/(2cs^4), -1/(2cs^2) are derived from these in the
+ * lattice dtype exactly as src/lbm.rs:54-56, :64-66, :84 compute them. */
+int chemsim_lbm_set_discretization(chemsim_lbm_t *h, double delta_x, double delta_t);
+
+/* collision = Box::new(BGK { tau })  (src/lbm.rs:345-347; factor = -dt/tau, :357) */
+int chemsim_lbm_set_bgk(chemsim_lbm_t *h, double tau);
+
+/* CollisionOperator::kinematic_shear_viscosity / _bulk_viscosity
+ * (src/lbm.rs:335-340, :366-369), computed in the lattice dtype. */
+int chemsim_lbm_kinematic_shear_viscosity(const chemsim_lbm_t *h, double *out);
+int chemsim_lbm_kinematic_bulk_viscosity(const chemsim_lbm_t *h, double *out);
+
+/* ---- state upload --------------------------------------------------------- */
+
+/* populations = compute_equilibrium(rho, (vx, vy), D2Q9::directions(), disc)
+ * followed by D2Q9::new (src/lbm.rs:43-71, main.rs:257-267), evaluated on the GPU. */
+int chemsim_lbm_init_equilibrium(chemsim_lbm_t *h, const void *rho, const void *vx, const void *vy,
+                                 size_t n);
+
+/* D2Q9::new(&[Population; 9]) one array at a time (src/lbm.rs:187-200); q in 0..9. */
+int chemsim_lbm_set_population(chemsim_lbm_t *h, int q, const void *src, size_t n);
+
+/* state.geometry = ... (src/lbm.rs:673; main.rs:269-312 and the live edit at
+ * main.rs:77-89): one byte per cell, non-zero = solid.  Callable between steps. */
+int chemsim_lbm_set_geometry(chemsim_lbm_t *h, const uint8_t *solid, size_t n);
+
+/* ---- the hot path --------------------------------------------------------- */
+
+/* State::step x nsteps (src/lbm.rs:694-714): stream -> bounce_back -> collide
+ * fused into one pass per step; time += dt per step.  Asynchronous. */
+int chemsim_lbm_step(chemsim_lbm_t *h, int nsteps);
+
+int chemsim_lbm_synchronize(chemsim_lbm_t *h);
+
+/* state.time (src/lbm.rs:671, :713), accumulated in the lattice dtype. */
+int chemsim_lbm_time(const chemsim_lbm_t *h, double *out);
+
+/* ---- macroscopic readout (device -> host on demand) ----------------------- */
+
+int chemsim_lbm_get_density(chemsim_lbm_t *h, void *dst, size_t n);          /* State::density  :779 -> :117 */
+int chemsim_lbm_get_pressure(chemsim_lbm_t *h, void *dst, size_t n);         /* State::pressure :784          */
+int chemsim_lbm_get_speed(chemsim_lbm_t *h, void *dst, size_t n);            /* State::speed    :800 -> :151 */
+int chemsim_lbm_get_velocity(chemsim_lbm_t *h, void *vx, void *vy, size_t n);         /* :795 -> :133 */
+int chemsim_lbm_get_momentum_density(chemsim_lbm_t *h, void *mx, void *my, size_t n); /* :790 -> :123 */
+int chemsim_lbm_get_population(chemsim_lbm_t *h, int q, void *dst, size_t n);         /* State::populations :769 */
+int chemsim_lbm_get_equilibrium(chemsim_lbm_t *h, int q, void *dst, size_t n);        /* State::equilibrium :805 */
+int chemsim_lbm_get_non_equilibrium(chemsim_lbm_t *h, int q, void *dst, size_t n);    /* State::non_equilibrium :810 */
+int chemsim_lbm_get_geometry(chemsim_lbm_t *h, uint8_t *dst, size_t n);               /* geometry.host(), main.rs:81 */
+
+/* Sum of all nine populations over this handle's cells, accumulated in f64
+ * (Matrix::sum -> af::sum_all, src/matrix.rs:138-140).  For a sharded lattice
+ * chemsim_lbm_total_mass_global all-reduces the slab sums over NCCL. */
+int chemsim_lbm_total_mass(chemsim_lbm_t *h, double *out);
+int chemsim_lbm_total_mass_global(chemsim_lbm_t *h, double *out);
+
+/* State::is_unstable (src/lbm.rs:815-818): min(f_eq,0) < 0 on this handle's cells. */
+int chemsim_lbm_is_unstable(chemsim_lbm_t *h, int *out);
+
+/* ---- interop / introspection ---------------------------------------------- */
+
+/* The cudaStream_t all of the handle's work is queued on (for CUDA-event timing
+ * by the caller). */
+int chemsim_lbm_cuda_stream(const chemsim_lbm_t *h, void **stream);
+
+/* Number of kernels this handle has launched since creation. */
+int chemsim_lbm_kernel_launches(const chemsim_lbm_t *h, uint64_t *out);
+
+/* Name of the fused step kernel variant the next chemsim_lbm_step will launch. */
+const char *chemsim_lbm_step_kernel_name(const chemsim_lbm_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEMSIM_LBM_H */

@@ -1,0 +1,278 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle
+on the same inputs.  Tolerances are BASELINE.json's: max relative error <= 1e-5
+(f32) / <= 1e-12 (f64); on top of that the kernels follow the reference's operation
+order without FMA contraction, so bit-equality with the oracle is asserted too.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from chemsim_b200 import lbm, scenarios
+from oracle import lbm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "d2q9_golden.npz"))
+DTYPES = [np.float32, np.float64]
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+def max_rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+
+
+def assert_parity(a, b, what=""):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape, what
+    err = max_rel_err(a, b)
+    assert err <= TOL[a.dtype], f"{what}: max rel err {err:g}"
+    u = np.uint32 if a.dtype == np.float32 else np.uint64
+    np.testing.assert_array_equal(np.ascontiguousarray(a).view(u), np.ascontiguousarray(b).view(u),
+                                  err_msg=f"{what}: not bit-identical")
+
+
+def make_state(rho, vx, vy, solid, tau, edge, dtype):
+    h, w = rho.shape
+    m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
+    disc = lbm.Discretization(1.0, 1.0)
+    pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
+    return lbm.State.initial(lbm.D2Q9.new(pops), solid, lbm.BGK(tau), disc, edge=edge)
+
+
+def check_all_fields(state, f_ref, what):
+    f = state.populations_array()
+    assert_parity(f, f_ref, what + " f")
+    assert_parity(state.density().array, O.density(f_ref), what + " rho")
+    ux, uy = state.velocity()
+    rux, ruy = O.velocity(f_ref)
+    assert_parity(ux.array, rux, what + " ux")
+    assert_parity(uy.array, ruy, what + " uy")
+    mass = state.total_mass()
+    ref_mass = O.total_mass(f_ref)
+    assert abs(mass - ref_mass) <= 1e-12 * abs(ref_mass), what + " mass"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_config1_main_rs_256_literal(dtype):
+    """BASELINE.json config 1 as SURVEY.md §8(d) makes it concrete: main.rs initial_state
+    at 256^2, BGK tau=15, zero-fill edges; gate N = 1, 2, 10, 50 incl. the mass series."""
+    rho, vx, vy, solid = scenarios.main_rs(256, 256, dtype)
+    state = make_state(rho, vx, vy, solid, 15.0, lbm.EDGE_ZEROFILL, dtype)
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    assert_parity(state.populations_array(), f_ref, "initial equilibrium")
+    col = O.collision(O.BGK, tau=15.0)
+    prev = 0
+    for n in (1, 2, 10, 50):
+        state.step(n - prev)
+        f_ref = O.step_ref(f_ref, solid, n - prev, col, O.EDGE_ZEROFILL)
+        prev = n
+        check_all_fields(state, f_ref, f"N={n}")
+    assert abs(state.time - 50.0) < 1e-6
+    if dtype == np.float64:   # SURVEY.md §6.2 derived known answers
+        assert abs(state.total_mass() - 65205.8375620200) < 1e-8
+        assert abs(state.population(1).array[128, 100] - 0.1161610097575969) < 1e-15
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_config1_stable_twin_periodic_1000_steps(dtype):
+    rho, vx, vy, solid = scenarios.main_rs(256, 256, dtype, walls=False)
+    state = make_state(rho, vx, vy, solid, 15.0, lbm.EDGE_PERIODIC, dtype)
+    m0 = state.total_mass()
+    state.step(1000)
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 1000, 15.0, O.EDGE_PERIODIC)
+    check_all_fields(state, f_ref, "N=1000")
+    drift = abs(state.total_mass() - m0) / m0
+    assert drift <= (1e-6 if dtype == np.float32 else 1e-12)
+    assert not state.is_unstable()
+
+
+def golden_bgk_cases():
+    for name in GOLDEN.files:
+        if "_bgk" in name:
+            yield name
+
+
+@pytest.mark.parametrize("name", list(golden_bgk_cases()))
+def test_golden_vectors(name):
+    dtype = np.float32 if "float32" in name else np.float64
+    n = int(name.split("_")[-1][1:])
+    if name.startswith("mainrs48_zerofill"):
+        (rho, vx, vy, solid), edge, tau = scenarios.main_rs(48, 48, dtype, True, 6.0), lbm.EDGE_ZEROFILL, 15.0
+    elif name.startswith("mainrs48_periodic"):
+        (rho, vx, vy, solid), edge, tau = scenarios.main_rs(48, 48, dtype, False, 6.0), lbm.EDGE_PERIODIC, 15.0
+    else:
+        edge = lbm.EDGE_PERIODIC if "_periodic_" in name else lbm.EDGE_ZEROFILL
+        (rho, vx, vy, solid), tau = scenarios.random_state(40, 24, dtype, seed=7), 0.8
+    state = make_state(rho, vx, vy, solid, tau, edge, dtype)
+    state.step(n)
+    assert_parity(state.populations_array(), GOLDEN[name], name)
+
+
+RAGGED = [(1, 1), (2, 1), (1, 5), (3, 2), (4, 4), (5, 3), (8, 1), (31, 7), (32, 3), (33, 2), (36, 5), (124, 3),
+          (127, 2), (128, 4), (129, 3), (132, 2), (260, 9), (1028, 3), (2052, 2)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("edge", [lbm.EDGE_ZEROFILL, lbm.EDGE_PERIODIC])
+def test_ragged_sizes_with_random_solids(dtype, edge):
+    """Edge cases: tiny, odd and non-multiple-of-vector widths (scalar kernel), widths
+    that end mid-warp and mid-block (vector kernel), single rows and columns."""
+    for (w, h) in RAGGED:
+        rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=w * 131 + h)
+        state = make_state(rho, vx, vy, solid, 0.8, edge, dtype)
+        state.step(3)
+        f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 3, 0.8, edge)
+        assert_parity(state.populations_array(), f_ref, f"{w}x{h} edge={edge}")
+        state.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_all_readouts(dtype):
+    rho, vx, vy, solid = scenarios.random_state(132, 37, dtype, seed=21)
+    state = make_state(rho, vx, vy, solid, 0.9, lbm.EDGE_PERIODIC, dtype)
+    state.step(4)
+    f = state.populations_array()
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 4, 0.9, O.EDGE_PERIODIC)
+    assert_parity(f, f_ref, "f")
+    assert_parity(state.density().array, O.density(f_ref), "density")
+    assert_parity(state.pressure().array, O.pressure(f_ref), "pressure")
+    assert_parity(state.speed().array, O.speed(f_ref), "speed")
+    for got, ref, name in zip(state.velocity(), O.velocity(f_ref), "xy"):
+        assert_parity(got.array, ref, "velocity " + name)
+    for got, ref, name in zip(state.momentum_density(), O.momentum_density(f_ref), "xy"):
+        assert_parity(got.array, ref, "momentum " + name)
+    feq_ref = O.lattice_equilibrium(f_ref)
+    feq = np.stack([m.array for _, m in state.equilibrium()])
+    assert_parity(feq, feq_ref, "equilibrium")
+    fneq = np.stack([m.array for _, m in state.non_equilibrium()])
+    assert_parity(fneq, f_ref - feq_ref, "non_equilibrium")
+    assert state.is_unstable() == O.is_unstable(f_ref)
+    assert abs(state.total_mass() - O.total_mass(f_ref)) <= 1e-12 * O.total_mass(f_ref)
+    np.testing.assert_array_equal(state.geometry, solid.astype(bool))
+    assert state.size() == (132, 37)
+
+
+def test_is_unstable_detects_negative_equilibrium():
+    dtype = np.float32
+    rho, vx, vy, solid = scenarios.main_rs(64, 64, dtype, walls=False, radius=0.0)
+    vx[10, 10] = 2.0      # |u| >> cs  ->  f_eq,0 = 4/9 rho (1 - 1.5 u^2) < 0
+    state = make_state(rho, vx, vy, solid, 1.0, lbm.EDGE_PERIODIC, dtype)
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    assert O.is_unstable(f_ref) and state.is_unstable()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_set_get_population_round_trip_and_explicit_populations(dtype):
+    rng = np.random.default_rng(5)
+    w, h = 100, 17
+    f0 = (0.05 + rng.random((9, h, w))).astype(dtype)
+    pops = [lbm.Matrix.new(f0[q].reshape(-1), (w, h), dtype=dtype) for q in range(9)]
+    solid = rng.random((h, w)) < 0.2
+    state = lbm.State.initial(lbm.D2Q9.new(pops), solid, lbm.BGK(1.3), lbm.Discretization(), edge=lbm.EDGE_ZEROFILL)
+    assert_parity(state.populations_array(), f0, "round trip")
+    state.step(2)
+    f_ref = O.step_ref(f0, solid.astype(np.uint8), 2, O.collision(O.BGK, tau=1.3), O.EDGE_ZEROFILL)
+    assert_parity(state.populations_array(), f_ref, "explicit populations")
+
+
+def test_geometry_can_be_rewritten_between_steps():
+    """main.rs:77-89 rewrites state.geometry while the simulation runs."""
+    dtype = np.float32
+    rho, vx, vy, solid = scenarios.main_rs(128, 128, dtype, walls=False, radius=0.0)
+    assert not solid.any()
+    state = make_state(rho, vx, vy, solid, 0.8, lbm.EDGE_PERIODIC, dtype)
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    state.step(3)
+    f_ref = O.step_fused(f_ref, solid, 3, 0.8, O.EDGE_PERIODIC)
+    solid2 = solid.copy()
+    solid2[60:69, 40:49] = 1          # the 9x9 block the mouse handler paints
+    state.geometry = solid2
+    state.step(5)
+    f_ref = O.step_fused(f_ref, solid2, 5, 0.8, O.EDGE_PERIODIC)
+    assert_parity(state.populations_array(), f_ref, "after geometry edit")
+    state.geometry = solid            # and removed again
+    state.step(2)
+    f_ref = O.step_fused(f_ref, solid, 2, 0.8, O.EDGE_PERIODIC)
+    assert_parity(state.populations_array(), f_ref, "after geometry removal")
+
+
+def test_discretization_other_than_unity():
+    dtype = np.float64
+    rho, vx, vy, solid = scenarios.random_state(64, 16, dtype, seed=4)
+    h, w = rho.shape
+    disc = lbm.Discretization(0.5, 0.25)
+    m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
+    pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
+    state = lbm.State.initial(lbm.D2Q9.new(pops), solid, lbm.BGK(0.4), disc, edge=lbm.EDGE_PERIODIC)
+    state.step(3)
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy, 0.5, 0.25), solid, 3, 0.4, O.EDGE_PERIODIC, 0.5, 0.25)
+    assert_parity(state.populations_array(), f_ref, "dx=0.5 dt=0.25")
+    assert abs(state.time - 0.75) < 1e-12
+
+
+def test_errors_mirror_the_reference():
+    state = lbm.State.create((32, 8), lbm.BGK(0.8))
+    with pytest.raises(lbm.LbmError) as e:
+        state.step()
+    assert e.value.status == 5  # NOT_READY: no populations yet
+    with pytest.raises(lbm.InvalidSliceSize):     # Matrix::new -> Err(InvalidSliceSize)
+        state.init_equilibrium(np.ones(10, np.float32), np.ones(10, np.float32), np.ones(10, np.float32))
+    with pytest.raises(lbm.InvalidSliceSize):
+        state.geometry = np.zeros((3, 3), bool)
+
+
+# ---- full-size, size-independent properties (BASELINE.json config 2 / 3 sizes) ----
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_full_size_4096_against_oracle_and_mass(dtype):
+    w = h = 4096
+    rho, vx, vy, solid = scenarios.smooth_periodic(w, h, dtype)
+    state = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+    state.init_equilibrium(rho, vx, vy)
+    assert "vec" in state.step_kernel_name()
+    m0 = state.total_mass()
+    state.step(2)
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), None, 2, 0.8, O.EDGE_PERIODIC)
+    for q in range(9):
+        assert_parity(state.population(q).array, f_ref[q], f"4096^2 q={q}")
+    state.step(98)
+    drift = abs(state.total_mass() - m0) / m0
+    assert drift <= (1e-6 if dtype == np.float32 else 1e-12), drift
+    assert not state.is_unstable()
+
+
+def test_full_size_uniform_state_is_a_fixed_point():
+    w = h = 4096
+    dtype = np.float32
+    rho = np.ones((h, w), dtype)
+    vx = np.full((h, w), 0.03, dtype)
+    vy = np.full((h, w), -0.02, dtype)
+    state = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+    state.init_equilibrium(rho, vx, vy)
+    f0 = state.population(5).array.copy()
+    state.step(50)
+    np.testing.assert_allclose(state.population(5).array, f0, rtol=2e-6)
+    np.testing.assert_allclose(state.density().array, 1.0, rtol=2e-6)
+
+
+def test_full_size_channel_8192x2048_transpose_isometry_and_oracle_band():
+    """Config 3: channel walls + cylinder.  (a) a band of rows around the cylinder is
+    compared with the oracle run on the whole lattice for 2 steps; (b) mass is conserved
+    (periodic in x, solid walls bounce everything back)."""
+    dtype = np.float32
+    w, h = 8192, 2048
+    rho, vx, vy, solid = scenarios.channel_cylinder(w, h, dtype)
+    state = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+    state.init_equilibrium(rho, vx, vy)
+    state.geometry = solid
+    m0 = state.total_mass()
+    state.step(2)
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 2, 0.8, O.EDGE_PERIODIC)
+    for q in range(9):
+        assert_parity(state.population(q).array, f_ref[q], f"channel q={q}")
+    state.step(200)
+    assert abs(state.total_mass() - m0) / m0 <= 1e-6
