@@ -154,7 +154,7 @@ def cpu_baseline(w, dtype_name, budget_s=12.0):
     dtype = NP_DTYPE[dtype_name]
     rows = 1024                                    # a (w x 1024) band of the lattice, periodic
     t1 = cpu_time_steps(w, rows, dtype, 1, 1)
-    steps = int(max(2, min(40, budget_s / max(t1, 1e-3))))
+    steps = int(max(2, min(2000, budget_s / max(t1, 1e-3))))
     dt = cpu_time_steps(w, rows, dtype, steps, 0)
     glups = w * rows * steps / dt / 1e9
     return {"value": glups, "unit": "GLUPS", "cores": O.max_threads(), "kind": "port",

@@ -22,15 +22,37 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float>  { using type = float4;  static constexpr int N = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
 
-__device__ __forceinline__ void load_vec(const float *p, float (&v)[4])
+// Predicated, branch-free global loads through the read-only path.  The source
+// buffer is never written by the kernel that reads it (A-B buffering), so .nc is
+// legal.  Predication instead of `if` keeps every load of a thread in ONE
+// straight-line batch: all of them are in flight before the first use.
+__device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4])
 {
-    const float4 t = *reinterpret_cast<const float4 *>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+        "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred));
 }
-__device__ __forceinline__ void load_vec(const double *p, double (&v)[2])
+__device__ __forceinline__ void ldg_vec(const double *p, bool pred, double (&v)[2])
 {
-    const double2 t = *reinterpret_cast<const double2 *>(p);
-    v[0] = t.x; v[1] = t.y;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
+        "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"
+        "@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n\t}"
+        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ float ldg_one(const float *p, bool pred)
+{
+    float v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=&f"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ double ldg_one(const double *p, bool pred)
+{
+    double v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
+        : "=&d"(v) : "l"(p), "r"((int)pred));
+    return v;
 }
 __device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
 {
@@ -40,15 +62,20 @@ __device__ __forceinline__ void store_vec(double *p, const double (&v)[2])
 {
     *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
 }
-__device__ __forceinline__ void load_mask(const uint8_t *p, bool (&s)[4])
+// V mask bytes as one 32-/16-bit word (0 when !pred)
+__device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const float *)
 {
-    const uchar4 t = *reinterpret_cast<const uchar4 *>(p);
-    s[0] = t.x != 0; s[1] = t.y != 0; s[2] = t.z != 0; s[3] = t.w != 0;
+    unsigned v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+        : "=&r"(v) : "l"(p), "r"((int)pred));
+    return v;
 }
-__device__ __forceinline__ void load_mask(const uint8_t *p, bool (&s)[2])
+__device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const double *)
 {
-    const uchar2 t = *reinterpret_cast<const uchar2 *>(p);
-    s[0] = t.x != 0; s[1] = t.y != 0;
+    unsigned short v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b16 %0, 0;\n\t@q ld.global.nc.u16 %0, [%1];\n\t}"
+        : "=&h"(v) : "l"(p), "r"((int)pred));
+    return v;
 }
 
 constexpr int STEP_THREADS = 256;
@@ -73,58 +100,63 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
     const int nvec = a.W / V;
     const bool active = xv < nvec;
     const int x0 = xv * V;
+    // which lanes must fetch the element their neighbour lane cannot supply
+    const bool first = xv == 0, last = xv == nvec - 1;
+    const bool need_left  = active && (lane == 0 || first)  && (PERIODIC_X || !first);
+    const bool need_right = active && (lane == 31 || last) && (PERIODIC_X || !last);
+    const int left_x  = first ? a.W - 1 : x0 - 1;    // wrap (periodic) or the previous warp's last element
+    const int right_x = last ? 0 : x0 + V;
 
-    T g[Q][V];
+    // ---- phase 1: every load of this thread, back to back ----------------------
+    T v[Q][V];      // the aligned vector of each population's source row
+    T e[Q];         // the one extra element for populations that stream along x
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         int sy = y - ey_of(q);
         if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
         const T *row = a.src + (size_t)q * a.plane + (size_t)(sy + 1) * a.pitch;
-        T v[V];
+        ldg_vec(row + x0, active, v[q]);
+        if (ex_of(q) == 1)       e[q] = ldg_one(row + left_x, need_left);
+        else if (ex_of(q) == -1) e[q] = ldg_one(row + right_x, need_right);
+        else                     e[q] = T(0);
+    }
+    unsigned maskw = 0;
+    if (HAS_MASK) maskw = ldg_mask(a.mask + (size_t)y * a.mask_pitch + x0, active, (const T *)nullptr);
+
+    // ---- phase 2: shift the x-streaming populations by one element -------------
+    T g[Q][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = T(0);
-        if (active) load_vec(row + x0, v);
+    for (int q = 0; q < Q; ++q) {
         if (ex_of(q) == 0) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) g[q][j] = v[j];
+            for (int j = 0; j < V; ++j) g[q][j] = v[q][j];
         } else if (ex_of(q) == 1) {                  // value at x comes from x−1
-            T left = __shfl_up_sync(0xffffffffu, v[V - 1], 1);
-            if (active && (lane == 0 || xv == 0)) {
-                if (xv > 0) left = row[x0 - 1];
-                else left = PERIODIC_X ? row[a.W - 1] : T(0);
-            }
-            g[q][0] = left;
+            const T nb = __shfl_up_sync(0xffffffffu, v[q][V - 1], 1);
+            g[q][0] = (lane == 0 || first) ? e[q] : nb;
 #pragma unroll
-            for (int j = 1; j < V; ++j) g[q][j] = v[j - 1];
+            for (int j = 1; j < V; ++j) g[q][j] = v[q][j - 1];
         } else {                                     // value at x comes from x+1
-            T right = __shfl_down_sync(0xffffffffu, v[0], 1);
-            if (active && (lane == 31 || xv == nvec - 1)) {
-                if (xv < nvec - 1) right = row[x0 + V];
-                else right = PERIODIC_X ? row[0] : T(0);
-            }
+            const T nb = __shfl_down_sync(0xffffffffu, v[q][0], 1);
 #pragma unroll
-            for (int j = 0; j < V - 1; ++j) g[q][j] = v[j + 1];
-            g[q][V - 1] = right;
+            for (int j = 0; j < V - 1; ++j) g[q][j] = v[q][j + 1];
+            g[q][V - 1] = (lane == 31 || last) ? e[q] : nb;
         }
     }
     if (!active) return;
 
-    bool solid[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) solid[j] = false;
-    if (HAS_MASK) load_mask(a.mask + (size_t)y * a.mask_pitch + x0, solid);
-
+    // ---- phase 3: bounce-back + collide, cell by cell ---------------------------
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         T c[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) c[q] = g[q][j];
-        if (HAS_MASK) bounce_back(c, solid[j]);
+        if (HAS_MASK) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
         collide_bgk(c, a.k);
 #pragma unroll
         for (int q = 0; q < Q; ++q) g[q][j] = c[q];
     }
 
+    // ---- phase 4: nine aligned vector stores ------------------------------------
     T *out = a.dst + (size_t)(y + 1) * a.pitch + x0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) store_vec(out + (size_t)q * a.plane, g[q]);
