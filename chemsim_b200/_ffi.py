@@ -71,6 +71,17 @@ PROTOTYPES = {
     "chemsim_lbm_step_kernel_name": (C.c_char_p, [_H]),
 }
 
+
+
+class HaloMsg(C.Structure):
+    _fields_ = [("is_send", C.c_int), ("peer", C.c_int), ("q", C.c_int), ("row", C.c_int)]
+
+
+HALO_PLAN_MAX = 12
+ROW_FIRST, ROW_LAST, ROW_GHOST_ABOVE, ROW_GHOST_BELOW = range(4)
+PROTOTYPES["chemsim_lbm_slab_rows"] = (_I, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I)])
+PROTOTYPES["chemsim_lbm_halo_plan"] = (_I, [_I, _I, _I, C.POINTER(HaloMsg), C.POINTER(_I)])
+
 _lib = None
 
 

@@ -157,24 +157,43 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_end)
     return a;
 }
 
-// Halo exchange of buffer b: populations moving towards larger y
-// (dy=+1: q = 3,6,7) go from my last row to the lower neighbour's ghost row −1;
-// populations moving towards smaller y (dy=−1: q = 1,5,8) go from my first row to
-// the upper neighbour's ghost row H.  Rows of one population are contiguous, so
-// the sends/receives work directly on the lattice buffers (no packing).
+// Halo plan: populations moving towards larger y (dy=+1: q = 3,6,7)
+// go from my last row to the lower neighbour's ghost row −1; populations moving
+// towards smaller y (dy=−1: q = 1,5,8) go from my first row to the upper
+// neighbour's ghost row H.  Sends are issued [to-lower, to-upper] and receives
+// [from-upper, from-lower], so that when both neighbours are the same rank
+// (nranks == 2, periodic) the k-th send to a peer matches its k-th receive.
+int build_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out)
+{
+    if (nranks <= 1) return 0;
+    const bool periodic = edge == CHEMSIM_LBM_EDGE_PERIODIC;
+    const int up = (rank + nranks - 1) % nranks, down = (rank + 1) % nranks;
+    const bool has_up = periodic || rank > 0, has_down = periodic || rank < nranks - 1;
+    static const int to_down[3] = {3, 6, 7}, to_up[3] = {1, 5, 8};
+    int n = 0;
+    if (has_down) for (int q : to_down) out[n++] = {1, down, q, CHEMSIM_LBM_ROW_LAST};
+    if (has_up)   for (int q : to_up)   out[n++] = {1, up, q, CHEMSIM_LBM_ROW_FIRST};
+    if (has_up)   for (int q : to_down) out[n++] = {0, up, q, CHEMSIM_LBM_ROW_GHOST_ABOVE};
+    if (has_down) for (int q : to_up)   out[n++] = {0, down, q, CHEMSIM_LBM_ROW_GHOST_BELOW};
+    return n;
+}
+
+// Rows of one population are contiguous, so the sends/receives work directly on
+// the lattice buffers (no packing); one ncclGroup = one fused NCCL kernel.
 int exchange(chemsim_lbm *h, int b)
 {
-    const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
-    const int up = (h->rank + h->nranks - 1) % h->nranks, down = (h->rank + 1) % h->nranks;
-    const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
+    chemsim_lbm_halo_msg plan[CHEMSIM_LBM_HALO_PLAN_MAX];
+    const int count = build_halo_plan(h->rank, h->nranks, h->edge, plan);
     const size_t bytes = (size_t)h->W * h->esize;
-    static const int to_down[3] = {3, 6, 7}, to_up[3] = {1, 5, 8};
     const NcclDyn &n = nccl_dyn();
     NCCL_TRY(h, n.GroupStart());
-    if (has_down) for (int q : to_down) NCCL_TRY(h, n.Send(row_ptr(h, b, q, h->H - 1), bytes, ncclChar, down, h->comm, h->comm_stream));
-    if (has_up)   for (int q : to_up)   NCCL_TRY(h, n.Send(row_ptr(h, b, q, 0), bytes, ncclChar, up, h->comm, h->comm_stream));
-    if (has_up)   for (int q : to_down) NCCL_TRY(h, n.Recv(row_ptr(h, b, q, -1), bytes, ncclChar, up, h->comm, h->comm_stream));
-    if (has_down) for (int q : to_up)   NCCL_TRY(h, n.Recv(row_ptr(h, b, q, h->H), bytes, ncclChar, down, h->comm, h->comm_stream));
+    for (int i = 0; i < count; ++i) {
+        const chemsim_lbm_halo_msg &m = plan[i];
+        const int y = m.row == CHEMSIM_LBM_ROW_FIRST ? 0 : m.row == CHEMSIM_LBM_ROW_LAST ? h->H - 1
+                    : m.row == CHEMSIM_LBM_ROW_GHOST_ABOVE ? -1 : h->H;
+        if (m.is_send) NCCL_TRY(h, n.Send(row_ptr(h, b, m.q, y), bytes, ncclChar, m.peer, h->comm, h->comm_stream));
+        else           NCCL_TRY(h, n.Recv(row_ptr(h, b, m.q, y), bytes, ncclChar, m.peer, h->comm, h->comm_stream));
+    }
     NCCL_TRY(h, n.GroupEnd());
     h->launches += 1;   // one fused NCCL send/recv kernel per group
     return 0;
@@ -302,8 +321,7 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
     if (!h) return fail(nullptr, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "out of host memory");
     h->W = width;
     h->Hglobal = global_height;
-    h->row0 = (int)(((long long)global_height * rank) / nranks);
-    h->H = (int)(((long long)global_height * (rank + 1)) / nranks) - h->row0;
+    chemsim_lbm_slab_rows(global_height, rank, nranks, &h->row0, &h->H);
     h->dtype = dtype; h->edge = edge; h->device = device; h->rank = rank; h->nranks = nranks;
     h->esize = dtype == CHEMSIM_LBM_F32 ? 4 : 8;
     const int per_line = (int)(128 / h->esize);
@@ -393,6 +411,24 @@ int chemsim_lbm_nccl_unique_id(void *out_id)
     const ncclResult_t r = n.GetUniqueId(&id);
     if (r != ncclSuccess) return fail(nullptr, CHEMSIM_LBM_ERR_NCCL, std::string("ncclGetUniqueId: ") + n.GetErrorString(r));
     std::memcpy(out_id, &id, sizeof(id));
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_slab_rows(int global_height, int rank, int nranks, int *row_offset, int *rows)
+{
+    if (global_height <= 0 || nranks < 1 || rank < 0 || rank >= nranks || global_height < nranks)
+        return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    const int r0 = (int)(((long long)global_height * rank) / nranks);
+    const int r1 = (int)(((long long)global_height * (rank + 1)) / nranks);
+    if (row_offset) *row_offset = r0;
+    if (rows) *rows = r1 - r0;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out, int *count)
+{
+    if (!out || !count || nranks < 1 || rank < 0 || rank >= nranks) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *count = build_halo_plan(rank, nranks, edge, out);
     return CHEMSIM_LBM_OK;
 }
 

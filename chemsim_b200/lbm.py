@@ -360,3 +360,19 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(_ffi.NCCL_ID_BYTES)
     _ffi.check(_ffi.load().chemsim_lbm_nccl_unique_id(buf), None)
     return buf.raw
+
+
+def slab_rows(global_height: int, rank: int, nranks: int):
+    """(row_offset, rows) of the y-slab `rank` owns (host-only)."""
+    r0, rows = C.c_int(), C.c_int()
+    _ffi.check(_ffi.load().chemsim_lbm_slab_rows(global_height, rank, nranks, C.byref(r0), C.byref(rows)), None)
+    return r0.value, rows.value
+
+
+def halo_plan(rank: int, nranks: int, edge: int):
+    """The per-step halo messages of one rank, in issue order (host-only):
+    list of (is_send, peer, q, row) with row one of _ffi.ROW_*."""
+    buf = (_ffi.HaloMsg * _ffi.HALO_PLAN_MAX)()
+    n = C.c_int()
+    _ffi.check(_ffi.load().chemsim_lbm_halo_plan(rank, nranks, edge, buf, C.byref(n)), None)
+    return [(bool(m.is_send), m.peer, m.q, m.row) for m in buf[: n.value]]

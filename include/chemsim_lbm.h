@@ -95,6 +95,26 @@ int chemsim_lbm_create_slab(int width, int global_height, int dtype, int edge, i
                             int nranks, const void *nccl_id, chemsim_lbm_t **out);
 int chemsim_lbm_nccl_unique_id(void *out_id /* CHEMSIM_LBM_NCCL_ID_BYTES */);
 
+/* Host-only helpers that expose the sharding logic (no GPU needed; the CPU tests
+ * drive a gloo emulation of the exchange with them).
+ * slab_rows: the rows rank `rank` owns.  halo_plan: the messages one rank issues
+ * per step, in issue order; `out` must hold CHEMSIM_LBM_HALO_PLAN_MAX entries. */
+typedef enum {
+    CHEMSIM_LBM_ROW_FIRST = 0,       /* local row 0            (send) */
+    CHEMSIM_LBM_ROW_LAST = 1,        /* local row H-1          (send) */
+    CHEMSIM_LBM_ROW_GHOST_ABOVE = 2, /* ghost row -1           (recv) */
+    CHEMSIM_LBM_ROW_GHOST_BELOW = 3  /* ghost row H            (recv) */
+} chemsim_lbm_halo_row;
+typedef struct {
+    int is_send; /* 1 = ncclSend, 0 = ncclRecv */
+    int peer;    /* rank of the neighbour */
+    int q;       /* population index 0..8 */
+    int row;     /* chemsim_lbm_halo_row */
+} chemsim_lbm_halo_msg;
+#define CHEMSIM_LBM_HALO_PLAN_MAX 12
+int chemsim_lbm_slab_rows(int global_height, int rank, int nranks, int *row_offset, int *rows);
+int chemsim_lbm_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out, int *count);
+
 int chemsim_lbm_destroy(chemsim_lbm_t *h); /* Drop for State */
 
 /* State::size (src/lbm.rs:753-756) and the slab this handle owns. */
