@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(STEP_THREADS)
 step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 {
     constexpr int V = VecOf<T>::N;
-    const int y = a.y_begin + blockIdx.x * blockDim.y + threadIdx.y;
-    if (y >= a.y_end) return;                        // warp-uniform
+    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
+    if (yi >= a.y_count) return;                     // warp-uniform
+    const int y = a.y_begin + yi * a.y_stride;
     const int lane = threadIdx.x & 31;
     const int xv = blockIdx.y * blockDim.x + threadIdx.x;
     const int nvec = a.W / V;
@@ -168,8 +169,9 @@ __global__ void __launch_bounds__(STEP_THREADS)
 step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
 {
     const int x = blockIdx.y * blockDim.x + threadIdx.x;
-    const int y = a.y_begin + blockIdx.x * blockDim.y + threadIdx.y;
-    if (y >= a.y_end || x >= a.W) return;
+    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
+    if (yi >= a.y_count || x >= a.W) return;
+    const int y = a.y_begin + yi * a.y_stride;
     T c[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -352,7 +354,7 @@ const char *step_kernel_name(const StepArgs<T> &a)
 template <typename T>
 int launch_step(const StepArgs<T> &a, cudaStream_t s)
 {
-    const int rows = a.y_end - a.y_begin;
+    const int rows = a.y_count;
     if (rows <= 0) return 0;
     if (use_vec(a)) {
         constexpr int V = VecOf<T>::N;

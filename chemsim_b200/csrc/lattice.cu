@@ -67,7 +67,7 @@ struct chemsim_lbm {
     int *h_flag = nullptr;        // pinned
 
     cudaStream_t stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_boundary = nullptr, ev_exchange = nullptr;
+    cudaEvent_t ev_face = nullptr, ev_interior = nullptr, ev_halo = nullptr;
     ncclComm_t comm = nullptr;
     bool ghosts_valid = false;
     bool have_populations = false;
@@ -137,7 +137,7 @@ template <> const Consts<float> &consts_of<float>(const chemsim_lbm *h) { return
 template <> const Consts<double> &consts_of<double>(const chemsim_lbm *h) { return h->k.d; }
 
 template <typename T>
-StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_end)
+StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stride = 1)
 {
     StepArgs<T> a;
     a.src = (const T *)h->buf[h->cur];
@@ -147,7 +147,8 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_end)
     a.W = h->W;
     a.H = h->H;
     a.y_begin = y_begin;
-    a.y_end = y_end;
+    a.y_count = y_count;
+    a.y_stride = y_stride;
     a.wrap_y = (h->edge == CHEMSIM_LBM_EDGE_PERIODIC && h->nranks == 1) ? 1 : 0;
     a.periodic_x = h->edge == CHEMSIM_LBM_EDGE_PERIODIC ? 1 : 0;
     a.mask = h->mask;
@@ -199,22 +200,37 @@ int exchange(chemsim_lbm *h, int b)
     return 0;
 }
 
-// Make the ghost rows of the current buffer valid (after an upload).
-int ensure_ghosts(chemsim_lbm *h)
+// Sharded stepping runs on two streams:
+//   stream      (normal priority)  interior rows 1 … H−2, which read no ghost row
+//   comm_stream (highest priority) the two face rows, then the NCCL exchange of them
+// Step n on either stream depends only on step n−1 of the other, so the face-row
+// kernel and the exchange of step n overlap with the interior kernel of step n:
+//   face(n)     after interior(n−1)  (reads rows 1, H−2)   and exchange(n−1) (same stream)
+//   interior(n) after face(n−1)      (reads rows 0, H−1)   and interior(n−1) (same stream)
+// (interior(n+1) overwrites rows 1 … H−2 of the buffer exchange(n−1) works on, but
+// the exchange only touches rows 0, H−1 and the ghost rows — disjoint.)
+// The high priority lets the small face/NCCL kernels take SM slots as soon as blocks
+// of the big interior kernel retire instead of queueing behind its whole grid.
+
+// Make the ghost rows of the current buffer valid (after an upload) and order the
+// halo stream after everything queued on the main stream so far.
+int begin_sharded(chemsim_lbm *h)
 {
-    if (h->nranks == 1 || h->ghosts_valid) return 0;
-    CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
-    const int r = exchange(h, h->cur);
-    if (r) return r;
-    CUDA_TRY(h, cudaEventRecord(h->ev_exchange, h->comm_stream));
-    h->ghosts_valid = true;
+    CUDA_TRY(h, cudaEventRecord(h->ev_interior, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_interior, 0));
+    if (!h->ghosts_valid) {
+        const int r = exchange(h, h->cur);
+        if (r) return r;
+        h->ghosts_valid = true;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
     return 0;
 }
 
 template <typename T>
 int step_impl(chemsim_lbm *h, int nsteps)
 {
+    if (nsteps == 0) return 0;
     if (h->nranks == 1) {
         for (int s = 0; s < nsteps; ++s) {
             LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H), h->stream));
@@ -222,23 +238,25 @@ int step_impl(chemsim_lbm *h, int nsteps)
         }
         return 0;
     }
-    const int r0 = ensure_ghosts(h);
+    const int r0 = begin_sharded(h);
     if (r0) return r0;
     for (int s = 0; s < nsteps; ++s) {
-        // 1. the two face rows need the ghost rows of `cur`: wait for its exchange
-        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_exchange, 0));
-        LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, 1), h->stream));
-        if (h->H > 1) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, h->H - 1, h->H), h->stream));
-        CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));
-        // 2. ship the new face rows on the side stream ...
-        CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+        // both waits refer to the events recorded for step s−1 (or by begin_sharded)
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_face, 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_interior, 0));
+        // halo stream: face rows {0, H−1} of step s, then ship them
+        LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H > 1 ? 2 : 1, h->H > 1 ? h->H - 1 : 1), h->comm_stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
         const int r = exchange(h, h->cur ^ 1);
         if (r) return r;
-        CUDA_TRY(h, cudaEventRecord(h->ev_exchange, h->comm_stream));
-        // 3. ... while the interior (which reads no ghost row) is updated
-        if (h->H > 2) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 1, h->H - 1), h->stream));
+        // main stream: interior of step s
+        if (h->H > 2) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 1, h->H - 2), h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_interior, h->stream));
         h->cur ^= 1;
     }
+    // later work on the main stream (readouts, uploads) sees the finished halo work
+    CUDA_TRY(h, cudaEventRecord(h->ev_halo, h->comm_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
     return 0;
 }
 
@@ -341,10 +359,13 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
     } while (0)
 
     CREATE_TRY(cudaSetDevice(device));
-    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming));
-    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_exchange, cudaEventDisableTiming));
+    int prio_least = 0, prio_greatest = 0;
+    CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CREATE_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least));
+    CREATE_TRY(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_greatest));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_face, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_interior, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
     const size_t buf_bytes = (size_t)Q * h->plane * h->esize;
     for (int b = 0; b < 2; ++b) {
         CREATE_TRY(cudaMalloc(&h->buf[b], buf_bytes));
@@ -447,8 +468,9 @@ int chemsim_lbm_destroy(chemsim_lbm_t *h)
     if (h->d_flag) cudaFree(h->d_flag);
     if (h->h_scalar) cudaFreeHost(h->h_scalar);
     if (h->h_flag) cudaFreeHost(h->h_flag);
-    if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
-    if (h->ev_exchange) cudaEventDestroy(h->ev_exchange);
+    if (h->ev_face) cudaEventDestroy(h->ev_face);
+    if (h->ev_interior) cudaEventDestroy(h->ev_interior);
+    if (h->ev_halo) cudaEventDestroy(h->ev_halo);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     delete h;
