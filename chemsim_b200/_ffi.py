@@ -49,7 +49,11 @@ PROTOTYPES = {
     "chemsim_lbm_kinematic_shear_viscosity": (_I, [_H, C.POINTER(_D)]),
     "chemsim_lbm_kinematic_bulk_viscosity": (_I, [_H, C.POINTER(_D)]),
     "chemsim_lbm_init_equilibrium": (_I, [_H, _P, _P, _P, _SZ]),
+    "chemsim_lbm_init_equilibrium_rows": (_I, [_H, _I, _I, _P, _P, _P, _SZ]),
     "chemsim_lbm_set_population": (_I, [_H, _I, _P, _SZ]),
+    "chemsim_lbm_set_geometry_rows": (_I, [_H, _I, _I, _P, _SZ]),
+    "chemsim_lbm_set_geometry_async": (_I, [_H, _P, _SZ]),
+    "chemsim_lbm_get_density_async": (_I, [_H, _P, _SZ]),
     "chemsim_lbm_set_geometry": (_I, [_H, _P, _SZ]),
     "chemsim_lbm_step": (_I, [_H, _I]),
     "chemsim_lbm_synchronize": (_I, [_H]),

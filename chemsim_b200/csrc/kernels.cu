@@ -99,8 +99,15 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
     const int lane = threadIdx.x & 31;
     const int xv = blockIdx.y * blockDim.x + threadIdx.x;
     const int nvec = a.W / V;
+    if (xv - lane >= nvec) return;                   // whole warp beyond the row
     const bool active = xv < nvec;
     const int x0 = xv * V;
+    // any solid cell in the 32*V cells of this warp?  (one or two 64-cell segments)
+    unsigned seg_flags = 0;
+    if (HAS_MASK) {
+        const uint8_t *fl = a.mask_flags + (size_t)y * a.flag_pitch + ((xv - lane) * V) / MASK_SEGMENT;
+        seg_flags = (V == 4) ? *reinterpret_cast<const unsigned short *>(fl) : *fl;
+    }
     // which lanes must fetch the element their neighbour lane cannot supply
     const bool first = xv == 0, last = xv == nvec - 1;
     const bool need_left  = active && (lane == 0 || first)  && (PERIODIC_X || !first);
@@ -122,7 +129,8 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
         else                     e[q] = T(0);
     }
     unsigned maskw = 0;
-    if (HAS_MASK) maskw = ldg_mask(a.mask + (size_t)y * a.mask_pitch + x0, active, (const T *)nullptr);
+    if (HAS_MASK && seg_flags != 0)                  // warp-uniform
+        maskw = ldg_mask(a.mask + (size_t)y * a.mask_pitch + x0, active, (const T *)nullptr);
 
     // ---- phase 2: shift the x-streaming populations by one element -------------
     T g[Q][V];
@@ -192,12 +200,13 @@ step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
 // ---- compute_equilibrium on the device (src/lbm.rs:43-71) --------------------
 template <typename T>
 __global__ void init_equilibrium_kernel(const T *rho, const T *vx, const T *vy, T *dst, size_t plane, int pitch,
-                                        int W, int H, const __grid_constant__ Consts<T> k)
+                                        int W, int row_begin, int rows, const __grid_constant__ Consts<T> k)
 {
     const int x = blockIdx.y * blockDim.x + threadIdx.x;
-    const int y = blockIdx.x;
-    if (x >= W || y >= H) return;
-    const size_t c = (size_t)y * W + x;
+    const int yr = blockIdx.x;
+    if (x >= W || yr >= rows) return;
+    const int y = row_begin + yr;
+    const size_t c = (size_t)yr * W + x;
     const T r = rho[c], ux = vx[c], uy = vy[c];
     const T v2 = add(mul(ux, ux), mul(uy, uy));
 #pragma unroll
@@ -313,16 +322,26 @@ unstable_kernel(const T *src, size_t plane, int pitch, int W, int H, const __gri
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// One thread per (row, 64-cell segment): flags[y][seg] = any solid cell in the segment.
+// Mask rows are padded with zeros to a multiple of 128 bytes, so whole 16-byte words
+// can be read.
 __global__ void __launch_bounds__(RED_THREADS)
-mask_any_kernel(const uint8_t *mask, int mask_pitch, int W, int H, int *flag)
+mask_flags_kernel(const uint8_t *mask, int mask_pitch, int W, int row_begin, int rows, uint8_t *flags, int flag_pitch,
+                  int *any)
 {
-    bool any = false;
-    const size_t cells = (size_t)W * H;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
-        const int y = (int)(c / W), x = (int)(c % W);
-        any |= mask[(size_t)y * mask_pitch + x] != 0;
+    const int segs = (W + MASK_SEGMENT - 1) / MASK_SEGMENT;
+    const size_t total = (size_t)rows * segs;
+    bool found = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = row_begin + (int)(i / segs), seg = (int)(i % segs);
+        const uint4 *p = reinterpret_cast<const uint4 *>(mask + (size_t)y * mask_pitch + (size_t)seg * MASK_SEGMENT);
+        unsigned acc = 0;
+#pragma unroll
+        for (int j = 0; j < MASK_SEGMENT / 16; ++j) { const uint4 t = p[j]; acc |= t.x | t.y | t.z | t.w; }
+        flags[(size_t)y * flag_pitch + seg] = acc != 0 ? 1 : 0;
+        found |= acc != 0;
     }
-    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+    if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) atomicOr(any, 1);
 }
 
 inline int check_launch()
@@ -386,11 +405,11 @@ int launch_step(const StepArgs<T> &a, cudaStream_t s)
 }
 
 template <typename T>
-int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane, int pitch, int W, int H,
-                            const Consts<T> &k, cudaStream_t s)
+int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane, int pitch, int W,
+                            int row_begin, int rows, const Consts<T> &k, cudaStream_t s)
 {
-    const dim3 block(256), grid(H, (W + 255) / 256);
-    init_equilibrium_kernel<T><<<grid, block, 0, s>>>(rho, vx, vy, dst, plane, pitch, W, H, k);
+    const dim3 block(256), grid(rows, (W + 255) / 256);
+    init_equilibrium_kernel<T><<<grid, block, 0, s>>>(rho, vx, vy, dst, plane, pitch, W, row_begin, rows, k);
     const int e = check_launch();
     return e ? e : 1;
 }
@@ -427,10 +446,12 @@ int launch_is_unstable(const T *src, size_t plane, int pitch, int W, int H, cons
     return e ? e : 1;
 }
 
-int launch_mask_any(const uint8_t *mask, int mask_pitch, int W, int H, int *flag, cudaStream_t s)
+int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin, int rows, uint8_t *flags,
+                      int flag_pitch, int *any, cudaStream_t s)
 {
-    const int blocks = reduction_blocks((size_t)W * H);
-    mask_any_kernel<<<blocks, RED_THREADS, 0, s>>>(mask, mask_pitch, W, H, flag);
+    const int segs = (W + MASK_SEGMENT - 1) / MASK_SEGMENT;
+    const int blocks = reduction_blocks((size_t)rows * segs);
+    mask_flags_kernel<<<blocks, RED_THREADS, 0, s>>>(mask, mask_pitch, W, row_begin, rows, flags, flag_pitch, any);
     const int e = check_launch();
     return e ? e : 1;
 }
@@ -438,7 +459,7 @@ int launch_mask_any(const uint8_t *mask, int mask_pitch, int W, int H, int *flag
 #define CHEMSIM_INSTANTIATE(T)                                                                                       \
     template int launch_step<T>(const StepArgs<T> &, cudaStream_t);                                                  \
     template const char *step_kernel_name<T>(const StepArgs<T> &);                                                   \
-    template int launch_init_equilibrium<T>(const T *, const T *, const T *, T *, size_t, int, int, int,             \
+    template int launch_init_equilibrium<T>(const T *, const T *, const T *, T *, size_t, int, int, int, int,        \
                                             const Consts<T> &, cudaStream_t);                                        \
     template int launch_readout<T>(const ReadoutArgs<T> &, cudaStream_t);                                            \
     template int launch_total_mass<T>(const T *, size_t, int, int, int, double *, double *, cudaStream_t);           \

@@ -25,6 +25,9 @@ struct StepArgs {
     const uint8_t *mask;   // H rows of mask_pitch bytes, non-zero = solid
     int mask_pitch;
     int has_mask;          // 0: no solid cell anywhere in this slab, mask not read
+    const uint8_t *mask_flags;  // per row, one byte per 64-cell segment: any solid cell in it?
+    int flag_pitch;             // (a warp of the vector kernel covers whole segments and skips
+                                //  the mask load when they are solid-free)
     Consts<T> k;
 };
 
@@ -49,8 +52,10 @@ struct ReadoutArgs {
 // launch counter) or a negative cudaError_t.
 template <typename T> int launch_step(const StepArgs<T> &a, cudaStream_t s);
 template <typename T> const char *step_kernel_name(const StepArgs<T> &a);
+// rows [row_begin, row_begin + rows) of the lattice from dense (pitch == W) fields of `rows` rows
 template <typename T> int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane,
-                                                  int pitch, int W, int H, const Consts<T> &k, cudaStream_t s);
+                                                  int pitch, int W, int row_begin, int rows, const Consts<T> &k,
+                                                  cudaStream_t s);
 template <typename T> int launch_readout(const ReadoutArgs<T> &a, cudaStream_t s);
 // partials: at least mass_partials_capacity() doubles; out: one double
 int mass_partials_capacity();
@@ -58,6 +63,9 @@ template <typename T> int launch_total_mass(const T *src, size_t plane, int pitc
                                             double *out, cudaStream_t s);
 template <typename T> int launch_is_unstable(const T *src, size_t plane, int pitch, int W, int H, const Consts<T> &k,
                                              int *flag, cudaStream_t s);
-int launch_mask_any(const uint8_t *mask, int mask_pitch, int W, int H, int *flag, cudaStream_t s);
+constexpr int MASK_SEGMENT = 64;   // cells per mask-flag byte
+// recompute the segment flags of rows [row_begin, row_begin + rows); *any |= 1 if a solid cell exists there
+int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin, int rows, uint8_t *flags,
+                      int flag_pitch, int *any, cudaStream_t s);
 
 }  // namespace chemsim

@@ -59,8 +59,16 @@ struct chemsim_lbm {
     int pitch = 0;      // elements
     uint8_t *mask = nullptr;
     int mask_pitch = 0;
-    int has_mask = 0;
-    void *stage[3] = {nullptr, nullptr, nullptr};   // dense W*H fields
+    int has_mask = 0;          // 0 = known solid-free (mask never read); 1 = consult the segment flags
+    uint8_t *mask_flags = nullptr;
+    int flag_pitch = 0;
+    void *stage[3] = {nullptr, nullptr, nullptr};   // dense staging fields (grown on demand)
+    size_t stage_bytes[3] = {0, 0, 0};
+    void *snap[2] = {nullptr, nullptr};             // full-field snapshots for asynchronous readouts
+    int snap_next = 0;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_mask = nullptr, ev_snap_ready[2] = {nullptr, nullptr},
+                ev_snap_done[2] = {nullptr, nullptr};
     double *d_partials = nullptr, *d_scalar = nullptr;
     int *d_flag = nullptr;
     double *h_scalar = nullptr;   // pinned
@@ -154,6 +162,8 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.mask = h->mask;
     a.mask_pitch = h->mask_pitch;
     a.has_mask = h->has_mask;
+    a.mask_flags = h->mask_flags;
+    a.flag_pitch = h->flag_pitch;
     a.k = consts_of<T>(h);
     return a;
 }
@@ -260,35 +270,102 @@ int step_impl(chemsim_lbm *h, int nsteps)
     return 0;
 }
 
-int upload_field(chemsim_lbm *h, void *dst_dense, const void *src)
+int ensure_stage(chemsim_lbm *h, int count, size_t bytes)
 {
-    CUDA_TRY(h, cudaMemcpyAsync(dst_dense, src, (size_t)h->W * h->H * h->esize, cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < count; ++i) {
+        if (h->stage_bytes[i] >= bytes) continue;
+        if (h->stage[i]) { CUDA_TRY(h, cudaStreamSynchronize(h->stream)); CUDA_TRY(h, cudaFree(h->stage[i])); }
+        h->stage[i] = nullptr; h->stage_bytes[i] = 0;
+        CUDA_TRY(h, cudaMalloc(&h->stage[i], bytes));
+        h->stage_bytes[i] = bytes;
+    }
     return 0;
 }
 
-int ensure_stage(chemsim_lbm *h, int count)
+template <typename T>
+ReadoutArgs<T> readout_args(const chemsim_lbm *h, int kind, int q, void *out0, void *out1)
 {
-    for (int i = 0; i < count; ++i)
-        if (!h->stage[i]) CUDA_TRY(h, cudaMalloc(&h->stage[i], (size_t)h->W * h->H * h->esize));
-    return 0;
+    ReadoutArgs<T> a;
+    a.src = (const T *)h->buf[h->cur];
+    a.plane = h->plane; a.pitch = h->pitch; a.W = h->W; a.H = h->H;
+    a.kind = kind; a.q = q;
+    a.out0 = (T *)out0; a.out1 = (T *)out1;
+    a.k = consts_of<T>(h);
+    return a;
 }
 
 template <typename T>
 int readout_impl(chemsim_lbm *h, int kind, int q, void *dst0, void *dst1)
 {
-    const int rs = ensure_stage(h, dst1 ? 2 : 1);
-    if (rs) return rs;
-    ReadoutArgs<T> a;
-    a.src = (const T *)h->buf[h->cur];
-    a.plane = h->plane; a.pitch = h->pitch; a.W = h->W; a.H = h->H;
-    a.kind = kind; a.q = q;
-    a.out0 = (T *)h->stage[0]; a.out1 = (T *)h->stage[1];
-    a.k = consts_of<T>(h);
-    LAUNCH_TRY(h, launch_readout<T>(a, h->stream));
     const size_t bytes = (size_t)h->W * h->H * sizeof(T);
+    const int rs = ensure_stage(h, dst1 ? 2 : 1, bytes);
+    if (rs) return rs;
+    LAUNCH_TRY(h, launch_readout<T>(readout_args<T>(h, kind, q, h->stage[0], h->stage[1]), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(dst0, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
     if (dst1) CUDA_TRY(h, cudaMemcpyAsync(dst1, h->stage[1], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Asynchronous density snapshot: the readout kernel runs on the main stream into
+// one of two snapshot buffers, the device->host copy on its own stream, so the
+// next steps overlap with the transfer (record/render "on demand").
+template <typename T>
+int density_async_impl(chemsim_lbm *h, void *dst)
+{
+    const size_t bytes = (size_t)h->W * h->H * sizeof(T);
+    const int slot = h->snap_next;
+    h->snap_next ^= 1;
+    if (!h->snap[slot]) CUDA_TRY(h, cudaMalloc(&h->snap[slot], bytes));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_snap_done[slot], 0));   // previous copy out of this slot
+    LAUNCH_TRY(h, launch_readout<T>(readout_args<T>(h, READ_DENSITY, 0, h->snap[slot], nullptr), h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_snap_ready[slot], h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_snap_ready[slot], 0));
+    CUDA_TRY(h, cudaMemcpyAsync(dst, h->snap[slot], bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_snap_done[slot], h->d2h_stream));
+    return 0;
+}
+
+int check_rows(chemsim_lbm *h, int row_begin, int row_count, size_t n)
+{
+    if (row_begin < 0 || row_count <= 0 || row_begin + row_count > h->H)
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "row range outside the slab");
+    if (n != (size_t)h->W * (size_t)row_count)
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE,
+                    "slice has " + std::to_string(n) + " elements, row range is " + std::to_string(h->W) + "x" +
+                        std::to_string(row_count));
+    return 0;
+}
+
+int init_equilibrium_rows(chemsim_lbm *h, int row_begin, int row_count, const void *rho, const void *vx, const void *vy)
+{
+    const size_t bytes = (size_t)h->W * row_count * h->esize;
+    const int rs = ensure_stage(h, 3, bytes);
+    if (rs) return rs;
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage[0], rho, bytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage[1], vx, bytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage[2], vy, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (h->dtype == CHEMSIM_LBM_F32)
+        LAUNCH_TRY(h, launch_init_equilibrium<float>((const float *)h->stage[0], (const float *)h->stage[1],
+                                                     (const float *)h->stage[2], (float *)h->buf[h->cur], h->plane,
+                                                     h->pitch, h->W, row_begin, row_count, h->k.f, h->stream));
+    else
+        LAUNCH_TRY(h, launch_init_equilibrium<double>((const double *)h->stage[0], (const double *)h->stage[1],
+                                                      (const double *)h->stage[2], (double *)h->buf[h->cur], h->plane,
+                                                      h->pitch, h->W, row_begin, row_count, h->k.d, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // the host buffers may be pageable / reused by the caller
+    h->have_populations = true;
+    h->ghosts_valid = false;
+    return CHEMSIM_LBM_OK;
+}
+
+// Upload mask rows on stream `s`, refresh their segment flags; *d_flag |= any solid.
+int upload_geometry_rows(chemsim_lbm *h, int row_begin, int row_count, const uint8_t *solid, cudaStream_t s)
+{
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->mask + (size_t)row_begin * h->mask_pitch, h->mask_pitch, solid, h->W, h->W,
+                                  row_count, cudaMemcpyHostToDevice, s));
+    LAUNCH_TRY(h, launch_mask_flags(h->mask, h->mask_pitch, h->W, row_begin, row_count, h->mask_flags, h->flag_pitch,
+                                    h->d_flag, s));
     return 0;
 }
 
@@ -346,6 +423,7 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
     h->pitch = ((width + per_line - 1) / per_line) * per_line;
     h->plane = (size_t)(h->H + 2) * h->pitch;
     h->mask_pitch = ((width + 127) / 128) * 128;
+    h->flag_pitch = (((width + MASK_SEGMENT - 1) / MASK_SEGMENT + 2 + 15) / 16) * 16;
     rebuild_scalars(h);
 
 #define CREATE_TRY(expr)                                                                        \
@@ -373,6 +451,16 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
     }
     CREATE_TRY(cudaMalloc((void **)&h->mask, (size_t)h->H * h->mask_pitch));
     CREATE_TRY(cudaMemsetAsync(h->mask, 0, (size_t)h->H * h->mask_pitch, h->stream));
+    CREATE_TRY(cudaMalloc((void **)&h->mask_flags, (size_t)h->H * h->flag_pitch));
+    CREATE_TRY(cudaMemsetAsync(h->mask_flags, 0, (size_t)h->H * h->flag_pitch, h->stream));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_mask, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CREATE_TRY(cudaEventCreateWithFlags(&h->ev_snap_ready[i], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&h->ev_snap_done[i], cudaEventDisableTiming));
+    }
     CREATE_TRY(cudaMalloc((void **)&h->d_partials, sizeof(double) * mass_partials_capacity()));
     CREATE_TRY(cudaMalloc((void **)&h->d_scalar, 2 * sizeof(double)));
     CREATE_TRY(cudaMalloc((void **)&h->d_flag, sizeof(int)));
@@ -461,8 +549,20 @@ int chemsim_lbm_destroy(chemsim_lbm_t *h)
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->comm) nccl_dyn().CommDestroy(h->comm);
     for (int b = 0; b < 2; ++b) if (h->buf[b]) cudaFree(h->buf[b]);
+    if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
     for (int i = 0; i < 3; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (h->snap[i]) cudaFree(h->snap[i]);
+        if (h->ev_snap_ready[i]) cudaEventDestroy(h->ev_snap_ready[i]);
+        if (h->ev_snap_done[i]) cudaEventDestroy(h->ev_snap_done[i]);
+    }
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
+    if (h->ev_mask) cudaEventDestroy(h->ev_mask);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->mask) cudaFree(h->mask);
+    if (h->mask_flags) cudaFree(h->mask_flags);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_scalar) cudaFree(h->d_scalar);
     if (h->d_flag) cudaFree(h->d_flag);
@@ -536,24 +636,28 @@ int chemsim_lbm_init_equilibrium(chemsim_lbm_t *h, const void *rho, const void *
     BIND(h);
     const int c = check_n(h, n);
     if (c) return c;
-    const int rs = ensure_stage(h, 3);
-    if (rs) return rs;
-    int r;
-    if ((r = upload_field(h, h->stage[0], rho)) || (r = upload_field(h, h->stage[1], vx)) ||
-        (r = upload_field(h, h->stage[2], vy)))
-        return r;
-    if (h->dtype == CHEMSIM_LBM_F32)
-        LAUNCH_TRY(h, launch_init_equilibrium<float>((const float *)h->stage[0], (const float *)h->stage[1],
-                                                     (const float *)h->stage[2], (float *)h->buf[h->cur], h->plane,
-                                                     h->pitch, h->W, h->H, h->k.f, h->stream));
-    else
-        LAUNCH_TRY(h, launch_init_equilibrium<double>((const double *)h->stage[0], (const double *)h->stage[1],
-                                                      (const double *)h->stage[2], (double *)h->buf[h->cur], h->plane,
-                                                      h->pitch, h->W, h->H, h->k.d, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // the host buffers may be pageable / reused by the caller
-    h->have_populations = true;
-    h->ghosts_valid = false;
+    // bounded staging: at most ~64 MiB per field on the device at a time
+    const size_t row_bytes = (size_t)h->W * h->esize;
+    int chunk = (int)((64u << 20) / row_bytes);
+    if (chunk < 1) chunk = 1;
+    for (int y = 0; y < h->H; y += chunk) {
+        const int rows = h->H - y < chunk ? h->H - y : chunk;
+        const size_t off = (size_t)y * row_bytes;
+        const int r = init_equilibrium_rows(h, y, rows, (const char *)rho + off, (const char *)vx + off,
+                                            (const char *)vy + off);
+        if (r) return r;
+    }
     return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_init_equilibrium_rows(chemsim_lbm_t *h, int row_begin, int row_count, const void *rho, const void *vx,
+                                      const void *vy, size_t n)
+{
+    if (!h || !rho || !vx || !vy) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_rows(h, row_begin, row_count, n);
+    if (c) return c;
+    return init_equilibrium_rows(h, row_begin, row_count, rho, vx, vy);
 }
 
 int chemsim_lbm_set_population(chemsim_lbm_t *h, int q, const void *src, size_t n)
@@ -577,12 +681,42 @@ int chemsim_lbm_set_geometry(chemsim_lbm_t *h, const uint8_t *solid, size_t n)
     BIND(h);
     const int c = check_n(h, n);
     if (c) return c;
-    CUDA_TRY(h, cudaMemcpy2DAsync(h->mask, h->mask_pitch, solid, h->W, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
-    LAUNCH_TRY(h, launch_mask_any(h->mask, h->mask_pitch, h->W, h->H, h->d_flag, h->stream));
+    const int r = upload_geometry_rows(h, 0, h->H, solid, h->stream);
+    if (r) return r;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->has_mask = *h->h_flag ? 1 : 0;
+    h->has_mask = *h->h_flag ? 1 : 0;   // a solid-free geometry takes the mask-free kernel
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_geometry_rows(chemsim_lbm_t *h, int row_begin, int row_count, const uint8_t *solid, size_t n)
+{
+    if (!h || !solid) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_rows(h, row_begin, row_count, n);
+    if (c) return c;
+    const int r = upload_geometry_rows(h, row_begin, row_count, solid, h->stream);
+    if (r) return r;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->has_mask = 1;                    // other rows may hold solids: consult the segment flags
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_geometry_async(chemsim_lbm_t *h, const uint8_t *solid, size_t n)
+{
+    if (!h || !solid) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    // the copy stream may not overwrite the mask while queued steps still read it
+    CUDA_TRY(h, cudaEventRecord(h->ev_main, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_main, 0));
+    const int r = upload_geometry_rows(h, 0, h->H, solid, h->h2d_stream);
+    if (r) return r;
+    CUDA_TRY(h, cudaEventRecord(h->ev_mask, h->h2d_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_mask, 0));
+    h->has_mask = 1;                    // not known on the host: the kernel consults the segment flags
     return CHEMSIM_LBM_OK;
 }
 
@@ -608,6 +742,8 @@ int chemsim_lbm_synchronize(chemsim_lbm_t *h)
     BIND(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->h2d_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     return CHEMSIM_LBM_OK;
 }
 
@@ -619,6 +755,16 @@ int chemsim_lbm_time(const chemsim_lbm_t *h, double *out)
 }
 
 int chemsim_lbm_get_density(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_DENSITY, 0, dst, nullptr, n); }
+int chemsim_lbm_get_density_async(chemsim_lbm_t *h, void *dst, size_t n)
+{
+    if (!h || !dst) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    BIND(h);
+    const int c = check_n(h, n);
+    if (c) return c;
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    return h->dtype == CHEMSIM_LBM_F32 ? density_async_impl<float>(h, dst) : density_async_impl<double>(h, dst);
+}
+
 int chemsim_lbm_get_pressure(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_PRESSURE, 0, dst, nullptr, n); }
 int chemsim_lbm_get_speed(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_SPEED, 0, dst, nullptr, n); }
 

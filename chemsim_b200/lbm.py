@@ -244,6 +244,15 @@ class State:
             raise InvalidSliceSize(_ffi.ERR_INVALID_SLICE_SIZE, "rho, vx, vy differ in size")
         self._check(self._lib.chemsim_lbm_init_equilibrium(self._h, prho, pvx, pvy, n))
 
+    def init_equilibrium_rows(self, row_begin, rho, vx, vy):
+        """init_equilibrium for rows [row_begin, row_begin + rho.shape[0]) only."""
+        rho, prho, n = self._in(rho)
+        vx, pvx, n1 = self._in(vx)
+        vy, pvy, n2 = self._in(vy)
+        if not (n == n1 == n2):
+            raise InvalidSliceSize(_ffi.ERR_INVALID_SLICE_SIZE, "rho, vx, vy differ in size")
+        self._check(self._lib.chemsim_lbm_init_equilibrium_rows(self._h, row_begin, n // self.width, prho, pvx, pvy, n))
+
     def set_population(self, q, field):
         a, p, n = self._in(field)
         self._check(self._lib.chemsim_lbm_set_population(self._h, q, p, n))
@@ -258,6 +267,19 @@ class State:
     def geometry(self, solid):
         a, p, n = self._in(np.asarray(solid).astype(np.uint8, copy=False), np.uint8)
         self._check(self._lib.chemsim_lbm_set_geometry(self._h, p, n))
+
+    def set_geometry_rows(self, row_begin, solid):
+        """Rewrite rows [row_begin, row_begin + solid.shape[0]) of the geometry."""
+        a, p, n = self._in(np.asarray(solid).astype(np.uint8, copy=False), np.uint8)
+        self._check(self._lib.chemsim_lbm_set_geometry_rows(self._h, row_begin, n // self.width, p, n))
+
+    def set_geometry_async(self, pinned_solid_ptr: int, n: int):
+        """Asynchronous upload from page-locked memory (pointer + element count)."""
+        self._check(self._lib.chemsim_lbm_set_geometry_async(self._h, C.c_void_p(pinned_solid_ptr), n))
+
+    def density_async(self, pinned_dst_ptr: int, n: int):
+        """Asynchronous State::density into page-locked memory; valid after synchronize()."""
+        self._check(self._lib.chemsim_lbm_get_density_async(self._h, C.c_void_p(pinned_dst_ptr), n))
 
     # ---- the hot path -----------------------------------------------------------
     def step(self, nsteps: int = 1):

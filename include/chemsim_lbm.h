@@ -143,12 +143,26 @@ int chemsim_lbm_kinematic_bulk_viscosity(const chemsim_lbm_t *h, double *out);
 int chemsim_lbm_init_equilibrium(chemsim_lbm_t *h, const void *rho, const void *vx, const void *vy,
                                  size_t n);
 
+/* The same for rows [row_begin, row_begin+row_count) of this handle's slab only
+ * (n = width*row_count): lets a caller initialise a lattice that is larger than
+ * the host memory it wants to spend, chunk by chunk. */
+int chemsim_lbm_init_equilibrium_rows(chemsim_lbm_t *h, int row_begin, int row_count, const void *rho,
+                                      const void *vx, const void *vy, size_t n);
+
 /* D2Q9::new(&[Population; 9]) one array at a time (src/lbm.rs:187-200); q in 0..9. */
 int chemsim_lbm_set_population(chemsim_lbm_t *h, int q, const void *src, size_t n);
 
 /* state.geometry = ... (src/lbm.rs:673; main.rs:269-312 and the live edit at
  * main.rs:77-89): one byte per cell, non-zero = solid.  Callable between steps. */
 int chemsim_lbm_set_geometry(chemsim_lbm_t *h, const uint8_t *solid, size_t n);
+/* Rewrites rows [row_begin, row_begin+row_count) of the geometry only (the mouse
+ * handler of main.rs:77-89 changes a 9x9 block but re-uploads everything). */
+int chemsim_lbm_set_geometry_rows(chemsim_lbm_t *h, int row_begin, int row_count, const uint8_t *solid,
+                                  size_t n);
+/* Asynchronous form: `solid` must be page-locked and stay valid until the next
+ * chemsim_lbm_synchronize(); the copy runs on its own stream and later steps wait
+ * for it on the device, the host does not block. */
+int chemsim_lbm_set_geometry_async(chemsim_lbm_t *h, const uint8_t *solid, size_t n);
 
 /* ---- the hot path --------------------------------------------------------- */
 
@@ -164,6 +178,10 @@ int chemsim_lbm_time(const chemsim_lbm_t *h, double *out);
 /* ---- macroscopic readout (device -> host on demand) ----------------------- */
 
 int chemsim_lbm_get_density(chemsim_lbm_t *h, void *dst, size_t n);          /* State::density  :779 -> :117 */
+/* Asynchronous State::density: snapshots the field on the device now and copies it
+ * to page-locked `dst` on a separate stream while later steps run; `dst` is valid
+ * after chemsim_lbm_synchronize().  At most two snapshots are in flight. */
+int chemsim_lbm_get_density_async(chemsim_lbm_t *h, void *dst, size_t n);
 int chemsim_lbm_get_pressure(chemsim_lbm_t *h, void *dst, size_t n);         /* State::pressure :784          */
 int chemsim_lbm_get_speed(chemsim_lbm_t *h, void *dst, size_t n);            /* State::speed    :800 -> :151 */
 int chemsim_lbm_get_velocity(chemsim_lbm_t *h, void *vx, void *vy, size_t n);         /* :795 -> :133 */

@@ -276,3 +276,73 @@ def test_full_size_channel_8192x2048_transpose_isometry_and_oracle_band():
         assert_parity(state.population(q).array, f_ref[q], f"channel q={q}")
     state.step(200)
     assert abs(state.total_mass() - m0) / m0 <= 1e-6
+
+
+# ---- chunked / asynchronous entry points ---------------------------------------------
+
+def test_row_chunked_init_and_geometry_equal_whole_field_calls():
+    dtype = np.float32
+    rho, vx, vy, solid = scenarios.random_state(192, 50, dtype, seed=31)
+    whole = make_state(rho, vx, vy, solid, 0.8, lbm.EDGE_PERIODIC, dtype)
+    parts = lbm.State.create((192, 50), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+    for r0, r1 in ((0, 7), (7, 32), (32, 50)):
+        parts.init_equilibrium_rows(r0, rho[r0:r1], vx[r0:r1], vy[r0:r1])
+        parts.set_geometry_rows(r0, solid[r0:r1])
+    whole.step(5)
+    parts.step(5)
+    assert_parity(parts.populations_array(), whole.populations_array(), "chunked upload")
+    np.testing.assert_array_equal(parts.geometry, solid.astype(bool))
+    with pytest.raises(lbm.LbmError):
+        parts.set_geometry_rows(45, solid[:10])           # row range outside the slab
+    with pytest.raises(lbm.InvalidSliceSize):
+        parts.init_equilibrium_rows(0, rho[:3], vx[:2], vy[:3])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_async_geometry_and_density_snapshots(dtype):
+    """The pipelined frame loop bench.py's e2e leg uses: asynchronous geometry upload,
+    step, asynchronous density snapshot into two alternating pinned buffers."""
+    import torch
+    w, h = 384, 70
+    rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=41, solid_fraction=0.02)
+    solid[:, 128:256] = 0                     # a solid-free band: exercises the segment-flag skip
+    state = make_state(rho, vx, vy, np.zeros_like(solid), 0.8, lbm.EDGE_PERIODIC, dtype)
+    masks = [solid, np.zeros_like(solid), solid[::-1].copy()]
+    pinned_masks = [torch.from_numpy(m.copy()).pin_memory() for m in masks]
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    out = [torch.empty((h, w), dtype=tdt).pin_memory() for _ in range(2)]
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    for i in range(6):
+        m = i % 3
+        state.set_geometry_async(pinned_masks[m].data_ptr(), pinned_masks[m].numel())
+        state.step(1)
+        state.density_async(out[i & 1].data_ptr(), out[i & 1].numel())
+        f_ref = O.step_fused(f_ref, masks[m], 1, 0.8, O.EDGE_PERIODIC)
+        if i >= 1:
+            pass
+        state.synchronize()
+        assert_parity(out[i & 1].numpy(), O.density(f_ref), f"async density frame {i}")
+    # without intermediate synchronisation: two snapshots in flight
+    for i in range(4):
+        state.set_geometry_async(pinned_masks[0].data_ptr(), pinned_masks[0].numel())
+        state.step(2)
+        state.density_async(out[i & 1].data_ptr(), out[i & 1].numel())
+        f_ref = O.step_fused(f_ref, masks[0], 2, 0.8, O.EDGE_PERIODIC)
+    state.synchronize()
+    assert_parity(out[1].numpy(), O.density(f_ref), "last snapshot")
+    assert_parity(state.populations_array(), f_ref, "populations after async frames")
+
+
+def test_solid_free_warps_skip_the_mask_but_results_are_identical():
+    """Geometry with solids only in a corner: most warps take the flag-skip path."""
+    dtype = np.float32
+    w, h = 1024, 24
+    rho, vx, vy, _ = scenarios.random_state(w, h, dtype, seed=51)
+    solid = np.zeros((h, w), np.uint8)
+    solid[3:6, 1000:1010] = 1
+    solid[20, 63] = 1
+    solid[21, 64] = 1
+    state = make_state(rho, vx, vy, solid, 0.8, lbm.EDGE_ZEROFILL, dtype)
+    state.step(6)
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 6, 0.8, O.EDGE_ZEROFILL)
+    assert_parity(state.populations_array(), f_ref, "sparse solids")
