@@ -61,6 +61,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HARNESS = os.path.join(HERE, "cpp", "main_rs_harness")
+
+
+def build_harness(force: bool = False) -> str:
+    """The C++ host mirror's driver (cpp/main_rs_harness.cpp), linked against the C-ABI library."""
+    build()
+    src = [os.path.join(HERE, "cpp", n) for n in ("main_rs_harness.cpp", "lbm.hpp")]
+    if not force and os.path.exists(HARNESS) and all(os.path.getmtime(s) < os.path.getmtime(HARNESS) for s in src + [LIB]):
+        return HARNESS
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", HARNESS, src[0], "-L" + HERE,
+           "-lchemsim_lbm", "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return HARNESS
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print(LIB)
+    print(build_harness(force="--force" in sys.argv))
