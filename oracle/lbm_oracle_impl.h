@@ -374,49 +374,84 @@ void FN(lbm_oracle_step_ref)(REAL *f, const uint8_t *solid, int w, int h, int ed
 
 /* ---- fused one-pass-per-step variant (BGK only), OpenMP over rows ----------
  * Same per-cell arithmetic in the same order as the three-pass version, so the
- * two are bit-identical; this is the all-cores CPU baseline that bench.py times.
- * y0/y1 with ghost rows let a caller emulate a y-slab (tests of the sharding
- * protocol): rows are addressed through `pitch_rows` = rows per population
- * plane, and row index -1 / h live at plane offsets 0 / h+1 when ghost==1.    */
+ * two are bit-identical (tests/test_oracle.py); this is the all-cores CPU
+ * baseline that bench.py times, so it is written the way one would write the
+ * CPU code for speed: row pointers hoisted, branch-free interior loop that the
+ * compiler vectorises (still one rounded IEEE operation per reference operation:
+ * -ffp-contract=off).  With ghost==1 the planes carry one ghost row above and
+ * below (rows -1 and h at plane rows 0 and h+1): a caller can emulate a y-slab. */
+static inline void FN(cell_bgk)(REAL *gq, int is_solid, const FN(consts_t) *k, REAL factor)
+{
+    /* State::bounce_back: g_i <- solid ? g_opp(i) : g_i */
+    const REAL g1 = is_solid ? gq[3] : gq[1], g3 = is_solid ? gq[1] : gq[3];
+    const REAL g2 = is_solid ? gq[4] : gq[2], g4 = is_solid ? gq[2] : gq[4];
+    const REAL g5 = is_solid ? gq[7] : gq[5], g7 = is_solid ? gq[5] : gq[7];
+    const REAL g6 = is_solid ? gq[8] : gq[6], g8 = is_solid ? gq[6] : gq[8];
+    gq[1] = g1; gq[2] = g2; gq[3] = g3; gq[4] = g4; gq[5] = g5; gq[6] = g6; gq[7] = g7; gq[8] = g8;
+    REAL rho = (REAL)0.0, mx = (REAL)0.0, my = (REAL)0.0;
+    for (int i = 0; i < 9; ++i) rho = rho + gq[i];
+    for (int i = 0; i < 9; ++i) { mx = mx + gq[i] * k->cx[i]; my = my + gq[i] * k->cy[i]; }
+    const REAL r = (REAL)1.0 / rho;
+    const REAL vx = r * mx, vy = r * my;
+    const REAL v2 = vx * vx + vy * vy;
+    for (int i = 0; i < 9; ++i) {
+        const REAL vc = vx * k->cx[i] + vy * k->cy[i];
+        const REAL vc2 = vc * vc;
+        const REAL sum = (((REAL)1.0 + vc * k->k1) + vc2 * k->k2) + v2 * k->k3;
+        const REAL fe = (rho * k->w[i]) * sum;
+        gq[i] = gq[i] + (gq[i] - fe) * factor;
+    }
+}
+
 void FN(lbm_oracle_step_fused)(const REAL *src, REAL *dst, const uint8_t *solid,
                                int w, int h, int edge, int ghost,
                                REAL dx, REAL dt, REAL tau)
 {
     FN(consts_t) k; FN(make_consts)(&k, dx, dt);
     const REAL factor = -dt / tau;
-    const size_t plane = (size_t)w * (h + 2 * (ghost ? 1 : 0));
     const int g = ghost ? 1 : 0;
+    const size_t plane = (size_t)w * (h + 2 * g);
+    REAL *zero_row = (REAL *)calloc((size_t)w, sizeof(REAL));
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < h; ++y) {
-        for (int x = 0; x < w; ++x) {
+        const REAL *row[9];
+        for (int i = 0; i < 9; ++i) {
+            int sy = y - ORACLE_EY[i];
+            if (!ghost && (sy < 0 || sy >= h)) {
+                if (edge == ORACLE_EDGE_PERIODIC) sy = (sy + h) % h;
+                else { row[i] = zero_row; continue; }
+            }
+            row[i] = src + (size_t)i * plane + (size_t)(sy + g) * w;
+        }
+        const uint8_t *srow = solid ? solid + (size_t)y * w : NULL;
+        REAL *out = dst + (size_t)(y + g) * w;
+        /* the two edge columns (and everything, for w < 3): generic wrap / zero-fill */
+        for (int pass = 0; pass < 2; ++pass) {
+            const int x = pass == 0 ? 0 : w - 1;
+            if (pass == 1 && w == 1) break;
             REAL gq[9];
             for (int i = 0; i < 9; ++i) {
-                int sy = y - ORACLE_EY[i], sx = x - ORACLE_EX[i];
+                int sx = x - ORACLE_EX[i];
                 int ok = 1;
                 if (sx < 0 || sx >= w) { if (edge == ORACLE_EDGE_PERIODIC) sx = (sx + w) % w; else ok = 0; }
-                if (!ghost && (sy < 0 || sy >= h)) { if (edge == ORACLE_EDGE_PERIODIC) sy = (sy + h) % h; else ok = 0; }
-                gq[i] = ok ? src[(size_t)i * plane + (size_t)(sy + g) * w + sx] : (REAL)0.0;
+                gq[i] = ok ? row[i][sx] : (REAL)0.0;
             }
-            if (solid && solid[(size_t)y * w + x]) {
-                REAL t;
-                t = gq[1]; gq[1] = gq[3]; gq[3] = t;
-                t = gq[2]; gq[2] = gq[4]; gq[4] = t;
-                t = gq[5]; gq[5] = gq[7]; gq[7] = t;
-                t = gq[6]; gq[6] = gq[8]; gq[8] = t;
-            }
-            REAL rho = (REAL)0.0, mx = (REAL)0.0, my = (REAL)0.0;
-            for (int i = 0; i < 9; ++i) rho = rho + gq[i];
-            for (int i = 0; i < 9; ++i) { mx = mx + gq[i] * k.cx[i]; my = my + gq[i] * k.cy[i]; }
-            REAL r = (REAL)1.0 / rho;
-            REAL vx = r * mx, vy = r * my;
-            REAL v2 = vx * vx + vy * vy;
-            for (int i = 0; i < 9; ++i) {
-                REAL vc = vx * k.cx[i] + vy * k.cy[i];
-                REAL vc2 = vc * vc;
-                REAL sum = (((REAL)1.0 + vc * k.k1) + vc2 * k.k2) + v2 * k.k3;
-                REAL fe = (rho * k.w[i]) * sum;
-                dst[(size_t)i * plane + (size_t)(y + g) * w + x] = gq[i] + (gq[i] - fe) * factor;
-            }
+            FN(cell_bgk)(gq, srow && srow[x], &k, factor);
+            for (int i = 0; i < 9; ++i) out[(size_t)i * plane + x] = gq[i];
+        }
+        /* interior columns: every source is in range */
+#pragma omp simd
+        for (int x = 1; x < w - 1; ++x) {
+            REAL gq[9];
+            gq[0] = row[0][x];     gq[1] = row[1][x];     gq[2] = row[2][x - 1];
+            gq[3] = row[3][x];     gq[4] = row[4][x + 1]; gq[5] = row[5][x - 1];
+            gq[6] = row[6][x - 1]; gq[7] = row[7][x + 1]; gq[8] = row[8][x + 1];
+            FN(cell_bgk)(gq, srow ? srow[x] : 0, &k, factor);
+            out[x] = gq[0];
+            out[plane + x] = gq[1];     out[2 * plane + x] = gq[2]; out[3 * plane + x] = gq[3];
+            out[4 * plane + x] = gq[4]; out[5 * plane + x] = gq[5]; out[6 * plane + x] = gq[6];
+            out[7 * plane + x] = gq[7]; out[8 * plane + x] = gq[8];
         }
     }
+    free(zero_row);
 }
