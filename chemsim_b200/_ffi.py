@@ -46,6 +46,9 @@ PROTOTYPES = {
     "chemsim_lbm_shape": (_I, [_H, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "chemsim_lbm_set_discretization": (_I, [_H, _D, _D]),
     "chemsim_lbm_set_bgk": (_I, [_H, _D]),
+    "chemsim_lbm_set_trt": (_I, [_H, _D, _D]),
+    "chemsim_lbm_set_regularized": (_I, [_H, _D]),
+    "chemsim_lbm_set_kbc": (_I, [_H, _D]),
     "chemsim_lbm_kinematic_shear_viscosity": (_I, [_H, C.POINTER(_D)]),
     "chemsim_lbm_kinematic_bulk_viscosity": (_I, [_H, C.POINTER(_D)]),
     "chemsim_lbm_init_equilibrium": (_I, [_H, _P, _P, _P, _SZ]),

@@ -88,7 +88,7 @@ constexpr int STEP_THREADS = 256;
 // aligned vector plus ONE element shuffled in from the adjacent lane; only the
 // first/last lane of a warp (or of the row) issues an extra scalar load, which
 // also implements the x edge (wrap or zero-fill).
-template <typename T, bool PERIODIC_X, bool HAS_MASK>
+template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
 __global__ void __launch_bounds__(STEP_THREADS)
 step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 {
@@ -160,7 +160,7 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 #pragma unroll
         for (int q = 0; q < Q; ++q) c[q] = g[q][j];
         if (HAS_MASK) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
-        collide_bgk(c, a.k);
+        collide<COL>(c, a.k);
 #pragma unroll
         for (int q = 0; q < Q; ++q) g[q][j] = c[q];
     }
@@ -172,7 +172,7 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 }
 
 // ---- the fused step, one cell per thread (any width) -------------------------
-template <typename T>
+template <typename T, int COL>
 __global__ void __launch_bounds__(STEP_THREADS)
 step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
 {
@@ -192,7 +192,7 @@ step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
         c[q] = inside ? a.src[(size_t)q * a.plane + (size_t)(sy + 1) * a.pitch + sx] : T(0);
     }
     if (a.has_mask) bounce_back(c, a.mask[(size_t)y * a.mask_pitch + x] != 0);
-    collide_bgk(c, a.k);
+    collide<COL>(c, a.k);
 #pragma unroll
     for (int q = 0; q < Q; ++q) a.dst[(size_t)q * a.plane + (size_t)(y + 1) * a.pitch + x] = c[q];
 }
@@ -370,11 +370,10 @@ const char *step_kernel_name(const StepArgs<T> &a)
     return sizeof(T) == 4 ? "step_vec_kernel<float>" : "step_vec_kernel<double>";
 }
 
-template <typename T>
-int launch_step(const StepArgs<T> &a, cudaStream_t s)
+template <typename T, int COL>
+void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
 {
     const int rows = a.y_count;
-    if (rows <= 0) return 0;
     if (use_vec(a)) {
         constexpr int V = VecOf<T>::N;
         const int nvec = a.W / V;
@@ -385,11 +384,11 @@ int launch_step(const StepArgs<T> &a, cudaStream_t s)
         const dim3 block(bx, by);
         const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
         if (a.periodic_x) {
-            if (a.has_mask) step_vec_kernel<T, true, true><<<grid, block, 0, s>>>(a);
-            else            step_vec_kernel<T, true, false><<<grid, block, 0, s>>>(a);
+            if (a.has_mask) step_vec_kernel<T, true, true, COL><<<grid, block, 0, s>>>(a);
+            else            step_vec_kernel<T, true, false, COL><<<grid, block, 0, s>>>(a);
         } else {
-            if (a.has_mask) step_vec_kernel<T, false, true><<<grid, block, 0, s>>>(a);
-            else            step_vec_kernel<T, false, false><<<grid, block, 0, s>>>(a);
+            if (a.has_mask) step_vec_kernel<T, false, true, COL><<<grid, block, 0, s>>>(a);
+            else            step_vec_kernel<T, false, false, COL><<<grid, block, 0, s>>>(a);
         }
     } else {
         int bx = ((a.W + 31) / 32) * 32;
@@ -398,7 +397,20 @@ int launch_step(const StepArgs<T> &a, cudaStream_t s)
         if (by > rows) by = rows;
         const dim3 block(bx, by);
         const dim3 grid((rows + by - 1) / by, (a.W + bx - 1) / bx);
-        step_scalar_kernel<T><<<grid, block, 0, s>>>(a);
+        step_scalar_kernel<T, COL><<<grid, block, 0, s>>>(a);
+    }
+}
+
+template <typename T>
+int launch_step(const StepArgs<T> &a, cudaStream_t s)
+{
+    if (a.y_count <= 0) return 0;
+    switch (a.collision) {
+    case COL_BGK:         launch_step_col<T, COL_BGK>(a, s); break;
+    case COL_TRT:         launch_step_col<T, COL_TRT>(a, s); break;
+    case COL_REGULARIZED: launch_step_col<T, COL_REGULARIZED>(a, s); break;
+    case COL_KBC:         launch_step_col<T, COL_KBC>(a, s); break;
+    default: return -(int)cudaErrorInvalidValue;
     }
     const int e = check_launch();
     return e ? e : 1;

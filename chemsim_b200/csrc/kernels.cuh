@@ -25,6 +25,7 @@ struct StepArgs {
     const uint8_t *mask;   // H rows of mask_pitch bytes, non-zero = solid
     int mask_pitch;
     int has_mask;          // 0: no solid cell anywhere in this slab, mask not read
+    int collision;         // Collision enum: which CollisionOperator the step applies
     const uint8_t *mask_flags;  // per row, one byte per 64-cell segment: any solid cell in it?
     int flag_pitch;             // (a warp of the vector kernel covers whole segments and skips
                                 //  the mask load when they are solid-free)

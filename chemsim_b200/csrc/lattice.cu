@@ -25,10 +25,17 @@ struct Scalars {   // host scalars in both dtypes, rebuilt whenever dx/dt/tau ch
     Consts<double> d;
 };
 
+struct CollisionParams {   // as given by the caller, converted to the lattice dtype in make_consts
+    int kind = COL_NONE;
+    double tau = 0.0;                      // BGK
+    double tau_plus = 0.0, tau_minus = 0.0;   // TRT
+    double viscosity = 0.0;                // KBC (and the viscosity a Regularized wrapper reports)
+};
+
 template <typename T>
-Consts<T> make_consts(double dx_, double dt_, double tau_)
+Consts<T> make_consts(double dx_, double dt_, const CollisionParams &c)
 {
-    Consts<T> k;
+    Consts<T> k{};
     static const int num[Q] = {16, 4, 4, 4, 4, 1, 1, 1, 1};
     for (int i = 0; i < Q; ++i) k.w[i] = (T)num[i] / (T)36.0;            // src/lbm.rs:209-219
     const T dx = (T)dx_, dt = (T)dt_;
@@ -38,7 +45,30 @@ Consts<T> make_consts(double dx_, double dt_, double tau_)
     k.k1 = (T)1.0 / k.cs2;                                                // :64
     k.k2 = (T)1.0 / ((T)2.0 * cs4);                                       // :65
     k.k3 = (T)-1.0 / ((T)2.0 * k.cs2);                                    // :66
-    k.factor = tau_ != 0.0 ? -dt / (T)tau_ : (T)0;                        // :357
+    k.factor = c.tau != 0.0 ? -dt / (T)c.tau : (T)0;                      // :357
+    // TRT, src/lbm.rs:428-439
+    k.omega_m = c.tau_minus != 0.0 ? (T)1.0 / (T)c.tau_minus : (T)0;
+    k.omega_p = c.tau_plus != 0.0 ? (T)1.0 / (T)c.tau_plus : (T)0;
+    k.half = -dt * (T)0.5;
+    // Regularized, src/lbm.rs:638-656
+    for (int i = 0; i < Q; ++i) {
+        const T cx = (T)cx_of(i), cy = (T)cy_of(i);
+        const T qxx = cx * cx - k.cs2, qxy = cx * cy, qyx = cy * cx, qyy = cy * cy - k.cs2;
+        const T sf = k.w[i] / ((T)2.0 * cs4);
+        k.axx[i] = qxx * sf; k.axy[i] = qxy * sf; k.ayx[i] = qyx * sf; k.ayy[i] = qyy * sf;
+    }
+    // KBC, src/lbm.rs:478-571
+    k.dx = dx;
+    k.dx2 = dx * dx;
+    k.dx_4 = dx * (T)4.0;
+    k.four_dx = (T)4.0 * dx;
+    k.two_dx2 = (T)2.0 * dx * dx;
+    k.neg_dx = -dx;
+    const T beta = (T)1.0 / (((T)2.0 * (T)c.viscosity / (cs * cs)) + (T)1.0);   // :547-550
+    k.neg_beta = -beta;
+    k.two_neg_beta = (T)2.0 * -beta;
+    k.gamma_scale = (T)2.0 - (T)1.0 / beta;
+    k.gamma_shift = (T)-1.0 / beta;
     return k;
 }
 
@@ -49,8 +79,8 @@ struct chemsim_lbm {
     int dtype = 0, edge = 0, device = 0;
     int rank = 0, nranks = 1;
     size_t esize = 4;
-    double dx = 1.0, dt = 1.0, tau = 0.0;
-    int collision = CHEMSIM_LBM_COLLISION_NONE;
+    double dx = 1.0, dt = 1.0;
+    CollisionParams col;
     Scalars k;
 
     void *buf[2] = {nullptr, nullptr};
@@ -131,8 +161,8 @@ int check_n(chemsim_lbm *h, size_t n)
 
 void rebuild_scalars(chemsim_lbm *h)
 {
-    h->k.f = make_consts<float>(h->dx, h->dt, h->tau);
-    h->k.d = make_consts<double>(h->dx, h->dt, h->tau);
+    h->k.f = make_consts<float>(h->dx, h->dt, h->col);
+    h->k.d = make_consts<double>(h->dx, h->dt, h->col);
 }
 
 char *row_ptr(chemsim_lbm *h, int b, int q, int y)
@@ -162,6 +192,7 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.mask = h->mask;
     a.mask_pitch = h->mask_pitch;
     a.has_mask = h->has_mask;
+    a.collision = h->col.kind;
     a.mask_flags = h->mask_flags;
     a.flag_pitch = h->flag_pitch;
     a.k = consts_of<T>(h);
@@ -600,23 +631,68 @@ int chemsim_lbm_set_bgk(chemsim_lbm_t *h, double tau)
 {
     if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
     if (tau == 0.0 || tau != tau) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "tau must be a non-zero number");
-    h->tau = tau;
-    h->collision = CHEMSIM_LBM_COLLISION_BGK;
+    h->col = CollisionParams();
+    h->col.kind = COL_BGK;
+    h->col.tau = tau;
     rebuild_scalars(h);
     return CHEMSIM_LBM_OK;
 }
 
+int chemsim_lbm_set_trt(chemsim_lbm_t *h, double tau_plus, double tau_minus)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (tau_plus == 0.0 || tau_minus == 0.0 || tau_plus != tau_plus || tau_minus != tau_minus)
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "tau_plus and tau_minus must be non-zero numbers");
+    h->col = CollisionParams();
+    h->col.kind = COL_TRT;
+    h->col.tau_plus = tau_plus;
+    h->col.tau_minus = tau_minus;
+    rebuild_scalars(h);
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_regularized(chemsim_lbm_t *h, double underlying_viscosity)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    h->col = CollisionParams();
+    h->col.kind = COL_REGULARIZED;
+    h->col.viscosity = underlying_viscosity;
+    rebuild_scalars(h);
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_kbc(chemsim_lbm_t *h, double ks_viscosity)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (ks_viscosity != ks_viscosity) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "viscosity is NaN");
+    h->col = CollisionParams();
+    h->col.kind = COL_KBC;
+    h->col.viscosity = ks_viscosity;
+    rebuild_scalars(h);
+    return CHEMSIM_LBM_OK;
+}
+
+extern "C++" {
+template <typename T>
+static T shear_viscosity(const chemsim_lbm *h)
+{
+    const T dx = (T)h->dx, dt = (T)h->dt;
+    switch (h->col.kind) {
+    case COL_BGK: return (dx * dx / ((T)3.0 * dt * dt)) * ((T)h->col.tau - dt / (T)2.0);   // src/lbm.rs:366-369
+    case COL_TRT: {                                                                          // :446-450
+        const T cs = dx / (std::sqrt((T)3.0) * dt);
+        return cs * cs * ((T)h->col.tau_plus / dt - (T)0.5);
+    }
+    default: return (T)h->col.viscosity;                                                     // :587-589, :663-665
+    }
+}
+}  // extern "C++"
+
 int chemsim_lbm_kinematic_shear_viscosity(const chemsim_lbm_t *h, double *out)
 {
     if (!h || !out) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
-    if (h->collision != CHEMSIM_LBM_COLLISION_BGK) return CHEMSIM_LBM_ERR_NOT_READY;
-    if (h->dtype == CHEMSIM_LBM_F32) {   // src/lbm.rs:366-369
-        const float dx = (float)h->dx, dt = (float)h->dt, tau = (float)h->tau;
-        *out = (double)((dx * dx / (3.0f * dt * dt)) * (tau - dt / 2.0f));
-    } else {
-        const double dx = h->dx, dt = h->dt, tau = h->tau;
-        *out = (dx * dx / (3.0 * dt * dt)) * (tau - dt / 2.0);
-    }
+    if (h->col.kind == COL_NONE) return CHEMSIM_LBM_ERR_NOT_READY;
+    *out = h->dtype == CHEMSIM_LBM_F32 ? (double)shear_viscosity<float>(h) : shear_viscosity<double>(h);
     return CHEMSIM_LBM_OK;
 }
 
@@ -725,7 +801,7 @@ int chemsim_lbm_step(chemsim_lbm_t *h, int nsteps)
     if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
     if (nsteps < 0) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "nsteps must be >= 0");
     if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set (init_equilibrium / set_population)");
-    if (h->collision == CHEMSIM_LBM_COLLISION_NONE) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "collision operator not set (set_bgk)");
+    if (h->col.kind == COL_NONE) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "collision operator not set (set_bgk / set_trt / set_regularized / set_kbc)");
     BIND(h);
     const int r = h->dtype == CHEMSIM_LBM_F32 ? step_impl<float>(h, nsteps) : step_impl<double>(h, nsteps);
     if (r) return r;

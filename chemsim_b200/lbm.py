@@ -106,6 +106,69 @@ class BGK:
         _ffi.check(_ffi.load().chemsim_lbm_set_bgk(handle, float(self.tau)), handle)
 
 
+@dataclass(frozen=True)
+class TRT:
+    """src/lbm.rs:374-451"""
+    tau_minus: float
+    tau_plus: float
+
+    @staticmethod
+    def new(lambda_, ks_viscosity, disc: Discretization, dtype=Scalar) -> "TRT":
+        """TRT::new(lambda, ks_viscosity, &disc), src/lbm.rs:380-390 (host arithmetic in Scalar)."""
+        t = np.dtype(dtype).type
+        dt = t(disc.delta_t)
+        cs = disc.isothermal_speed_of_sound(dtype)
+        tau_plus = dt * ((t(ks_viscosity) / (cs * cs)) + t(0.5))
+        tau_minus = dt * ((t(lambda_) / ((tau_plus / dt) - t(0.5))) + t(0.5))
+        return TRT(tau_minus=float(tau_minus), tau_plus=float(tau_plus))
+
+    def lambda_(self, disc: Discretization, dtype=Scalar):
+        t = np.dtype(dtype).type
+        dt = t(disc.delta_t)
+        return t(1.0) * ((t(self.tau_plus) / dt) - t(0.5)) * ((t(self.tau_minus) / dt) - t(0.5))
+
+    def kinematic_shear_viscosity(self, disc: Discretization, dtype=Scalar):
+        t = np.dtype(dtype).type
+        cs = disc.isothermal_speed_of_sound(dtype)
+        return cs * cs * (t(self.tau_plus) / t(disc.delta_t) - t(0.5))
+
+    def _apply(self, handle):
+        _ffi.check(_ffi.load().chemsim_lbm_set_trt(handle, float(self.tau_plus), float(self.tau_minus)), handle)
+
+
+@dataclass(frozen=True)
+class KBC:
+    """src/lbm.rs:455-590"""
+    ks_viscosity: float
+
+    @staticmethod
+    def new(ks_viscosity) -> "KBC":
+        return KBC(ks_viscosity)
+
+    def kinematic_shear_viscosity(self, disc: Discretization, dtype=Scalar):
+        return np.dtype(dtype).type(self.ks_viscosity)
+
+    def _apply(self, handle):
+        _ffi.check(_ffi.load().chemsim_lbm_set_kbc(handle, float(self.ks_viscosity)), handle)
+
+
+@dataclass(frozen=True)
+class Regularized:
+    """src/lbm.rs:596-666: wraps an operator but only ever uses its viscosity."""
+    underlying: object
+
+    @staticmethod
+    def new(underlying) -> "Regularized":
+        return Regularized(underlying)
+
+    def kinematic_shear_viscosity(self, disc: Discretization, dtype=Scalar):
+        return self.underlying.kinematic_shear_viscosity(disc, dtype)
+
+    def _apply(self, handle):
+        nu = float(self.underlying.kinematic_shear_viscosity(Discretization(), Scalar))
+        _ffi.check(_ffi.load().chemsim_lbm_set_regularized(handle, nu), handle)
+
+
 class EquilibriumPopulations:
     """Result of compute_equilibrium: the nine equilibrium populations of (rho, u),
     kept as their generating fields so that they are evaluated on the GPU when the

@@ -65,9 +65,12 @@ typedef enum {
     CHEMSIM_LBM_ERR_UNSUPPORTED = 6
 } chemsim_lbm_status;
 
-typedef enum {                     /* CollisionOperator impls, src/lbm.rs:327-666 */
+typedef enum {                            /* CollisionOperator impls, src/lbm.rs:327-666 */
     CHEMSIM_LBM_COLLISION_NONE = 0,
-    CHEMSIM_LBM_COLLISION_BGK = 1  /* src/lbm.rs:345-370 */
+    CHEMSIM_LBM_COLLISION_BGK = 1,        /* src/lbm.rs:345-370 */
+    CHEMSIM_LBM_COLLISION_TRT = 2,        /* src/lbm.rs:374-451 */
+    CHEMSIM_LBM_COLLISION_REGULARIZED = 3,/* src/lbm.rs:596-666 */
+    CHEMSIM_LBM_COLLISION_KBC = 4         /* src/lbm.rs:455-590 */
 } chemsim_lbm_collision;
 
 /* ---- library -------------------------------------------------------------- */
@@ -130,6 +133,19 @@ int chemsim_lbm_set_discretization(chemsim_lbm_t *h, double delta_x, double delt
 
 /* collision = Box::new(BGK { tau })  (src/lbm.rs:345-347; factor = -dt/tau, :357) */
 int chemsim_lbm_set_bgk(chemsim_lbm_t *h, double tau);
+
+/* collision = Box::new(TRT { tau_plus, tau_minus })  (src/lbm.rs:374-377; evaluate :401-444,
+ * including the swap_equilibrium quirk of :311-322).  TRT::new(lambda, viscosity, &disc)
+ * (:380-390) is host arithmetic the caller's shim performs. */
+int chemsim_lbm_set_trt(chemsim_lbm_t *h, double tau_plus, double tau_minus);
+
+/* collision = Box::new(Regularized::new(underlying))  (src/lbm.rs:596-666).  evaluate never
+ * calls the underlying operator; only its viscosity is reported (:663-665). */
+int chemsim_lbm_set_regularized(chemsim_lbm_t *h, double underlying_viscosity);
+
+/* collision = Box::new(KBC::new(ks_viscosity))  (src/lbm.rs:455-590; the DEBUG residual
+ * print of :575-582 is not reproduced). */
+int chemsim_lbm_set_kbc(chemsim_lbm_t *h, double ks_viscosity);
 
 /* CollisionOperator::kinematic_shear_viscosity / _bulk_viscosity
  * (src/lbm.rs:335-340, :366-369), computed in the lattice dtype. */

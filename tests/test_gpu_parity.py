@@ -346,3 +346,79 @@ def test_solid_free_warps_skip_the_mask_but_results_are_identical():
     state.step(6)
     f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 6, 0.8, O.EDGE_ZEROFILL)
     assert_parity(state.populations_array(), f_ref, "sparse solids")
+
+
+# ---- the other CollisionOperator impls of lbm.rs -------------------
+
+def _operators(dtype):
+    disc = lbm.Discretization(1.0, 1.0)
+    trt = lbm.TRT.new(0.25, 0.1, disc, dtype)
+    return {
+        "trt": (trt, O.collision(O.TRT, tau_plus=trt.tau_plus, tau_minus=trt.tau_minus)),
+        "regularized": (lbm.Regularized.new(lbm.KBC.new(10.0)), O.collision(O.REGULARIZED)),
+        "kbc": (lbm.KBC.new(0.1), O.collision(O.KBC, viscosity=0.1)),
+    }
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("edge", [lbm.EDGE_ZEROFILL, lbm.EDGE_PERIODIC])
+@pytest.mark.parametrize("name", ["trt", "regularized", "kbc"])
+def test_other_collision_operators_match_oracle(name, edge, dtype):
+    op, ocol = _operators(dtype)[name]
+    for (w, h) in ((40, 24), (37, 9), (256, 12)):       # vector kernel, scalar kernel, multi-warp rows
+        rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=w + h)
+        m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
+        disc = lbm.Discretization(1.0, 1.0)
+        pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
+        state = lbm.State.initial(lbm.D2Q9.new(pops), solid, op, disc, edge=edge)
+        state.step(3)
+        f_ref = O.step_ref(O.compute_equilibrium(rho, vx, vy), solid, 3, ocol, edge)
+        assert np.isfinite(f_ref).all()
+        assert_parity(state.populations_array(), f_ref, f"{name} {w}x{h}")
+        state.close()
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN.files if "_bgk" not in n])
+def test_golden_vectors_other_operators(name):
+    dtype = np.float32 if "float32" in name else np.float64
+    n = int(name.split("_")[-1][1:])
+    kind = name.split("_")[2]
+    op = {"trt": lbm.TRT(tau_minus=1.1, tau_plus=0.8), "regularized": lbm.Regularized.new(lbm.KBC.new(10.0)),
+          "kbc": lbm.KBC.new(0.1)}[kind]
+    rho, vx, vy, solid = scenarios.random_state(40, 24, dtype, seed=7)
+    h, w = rho.shape
+    m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
+    disc = lbm.Discretization(1.0, 1.0)
+    pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
+    state = lbm.State.initial(lbm.D2Q9.new(pops), solid, op, disc, edge=lbm.EDGE_PERIODIC)
+    state.step(n)
+    assert_parity(state.populations_array(), GOLDEN[name], name)
+
+
+def test_main_rs_active_configuration_regularized_kbc_400():
+    """What the reference's binary actually runs (src/main.rs:198-199, :343): 400x400,
+    Regularized<KBC(viscosity 10)>, zero-fill edges, walls + cylinder."""
+    dtype = np.float32
+    w = h = 400
+    rho, vx, vy, solid = scenarios.main_rs(w, h, dtype)
+    m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
+    disc = lbm.Discretization(1.0, 1.0)
+    collision = lbm.Regularized.new(lbm.KBC.new(10.0))
+    assert collision.kinematic_shear_viscosity(disc) == np.float32(10.0)
+    pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
+    state = lbm.State.initial(lbm.D2Q9.new(pops), solid, collision, disc)
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    prev = 0
+    for n in (1, 2, 10, 40):
+        state.step(n - prev)
+        f_ref = O.step_ref(f_ref, solid, n - prev, O.collision(O.REGULARIZED), O.EDGE_ZEROFILL)
+        prev = n
+        check_all_fields(state, f_ref, f"regularized N={n}")
+
+
+def test_trt_host_scalars():
+    disc = lbm.Discretization(1.0, 1.0)
+    trt = lbm.TRT.new(0.25, 10.0, disc)          # main.rs:189-190
+    assert np.float32(trt.tau_plus) == np.float32(1.0) * (np.float32(10.0) / (np.float32(0.577350259) ** 2) + np.float32(0.5))
+    assert abs(float(trt.lambda_(disc)) - 0.25) < 1e-6
+    assert abs(float(trt.kinematic_shear_viscosity(disc)) - 10.0) < 1e-5
