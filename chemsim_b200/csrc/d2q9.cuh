@@ -60,6 +60,9 @@ __device__ __forceinline__ float  sub(float a, float b)   { return __fsub_rn(a, 
 __device__ __forceinline__ float  mul(float a, float b)   { return __fmul_rn(a, b); }
 __device__ __forceinline__ float  divi(float a, float b)  { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float  root(float a)           { return __fsqrt_rn(a); }
+// correctly rounded reciprocal == IEEE 1/x (what af::div(1, x) yields), cheaper than a general division
+__device__ __forceinline__ float  recip(float a)          { return __frcp_rn(a); }
+__device__ __forceinline__ double recip(double a)         { return __drcp_rn(a); }
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -101,7 +104,7 @@ __device__ __forceinline__ Moments<T> moments(const T (&g)[Q])
     Moments<T> m;
     m.rho = density(g);
     momentum(g, m.mx, m.my);
-    const T r = divi(T(1), m.rho);
+    const T r = recip(m.rho);                       // 1/rho, Matrix::recip
     m.vx = mul(r, m.mx);
     m.vy = mul(r, m.my);
     return m;

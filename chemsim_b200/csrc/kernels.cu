@@ -88,12 +88,14 @@ constexpr int STEP_THREADS = 256;
 // aligned vector plus ONE element shuffled in from the adjacent lane; only the
 // first/last lane of a warp (or of the row) issues an extra scalar load, which
 // also implements the x edge (wrap or zero-fill).
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
+template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
 __global__ void __launch_bounds__(STEP_THREADS)
 step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 {
     constexpr int V = VecOf<T>::N;
-    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
+    // MULTIROW=false: one row per block (blockDim.y == 1), so the row index and all
+    // nine source-row addresses are block-uniform and live in uniform registers.
+    const int yi = MULTIROW ? blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
     if (yi >= a.y_count) return;                     // warp-uniform
     const int y = a.y_begin + yi * a.y_stride;
     const int lane = threadIdx.x & 31;
@@ -383,13 +385,17 @@ void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
         if (by > rows) by = rows;
         const dim3 block(bx, by);
         const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
+#define CHEMSIM_LAUNCH_VEC(PX, HM)                                                                   \
+        do {                                                                                         \
+            if (by == 1) step_vec_kernel<T, PX, HM, COL, false><<<grid, block, 0, s>>>(a);           \
+            else         step_vec_kernel<T, PX, HM, COL, true><<<grid, block, 0, s>>>(a);            \
+        } while (0)
         if (a.periodic_x) {
-            if (a.has_mask) step_vec_kernel<T, true, true, COL><<<grid, block, 0, s>>>(a);
-            else            step_vec_kernel<T, true, false, COL><<<grid, block, 0, s>>>(a);
+            if (a.has_mask) CHEMSIM_LAUNCH_VEC(true, true); else CHEMSIM_LAUNCH_VEC(true, false);
         } else {
-            if (a.has_mask) step_vec_kernel<T, false, true, COL><<<grid, block, 0, s>>>(a);
-            else            step_vec_kernel<T, false, false, COL><<<grid, block, 0, s>>>(a);
+            if (a.has_mask) CHEMSIM_LAUNCH_VEC(false, true); else CHEMSIM_LAUNCH_VEC(false, false);
         }
+#undef CHEMSIM_LAUNCH_VEC
     } else {
         int bx = ((a.W + 31) / 32) * 32;
         if (bx > STEP_THREADS) bx = STEP_THREADS;
