@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libchemsim_lbm.so")
+# CHEMSIM_LBM_LIB selects an experimental build of the same library (tools/variants.sh)
+LIB_PATH = os.environ.get("CHEMSIM_LBM_LIB") or os.path.join(HERE, "libchemsim_lbm.so")
 
 F32, F64 = 0, 1
 EDGE_ZEROFILL, EDGE_PERIODIC = 0, 1

@@ -44,6 +44,22 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experimental build with extra -D switches -> chemsim_b200/libchemsim_lbm_<name>.so
+    (select at run time with CHEMSIM_LBM_LIB=<path>; used by tools/variants.sh)."""
+    out = os.path.join(HERE, f"libchemsim_lbm_{name}.so")
+    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-ccbin", "g++", "-o", out,
+           *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    env = dict(os.environ)
+    env["PATH"] = "/usr/bin:" + env.get("PATH", "")
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(os.path.join(HERE, f"build_{name}.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB

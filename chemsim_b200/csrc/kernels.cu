@@ -22,6 +22,12 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float>  { using type = float4;  static constexpr int N = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
 
+#ifdef CHEMSIM_LOAD_NOALLOC
+#define CHEMSIM_LD_HINT ".L1::no_allocate"
+#else
+#define CHEMSIM_LD_HINT ""
+#endif
+
 // Predicated, branch-free global loads through the read-only path.  The source
 // buffer is never written by the kernel that reads it (A-B buffering), so .nc is
 // legal.  Predication instead of `if` keeps every load of a thread in ONE
@@ -30,14 +36,14 @@ __device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4]
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
         "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
-        "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        "@q ld.global.nc" CHEMSIM_LD_HINT ".v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
         : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred));
 }
 __device__ __forceinline__ void ldg_vec(const double *p, bool pred, double (&v)[2])
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
         "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"
-        "@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n\t}"
+        "@q ld.global.nc" CHEMSIM_LD_HINT ".v2.f64 {%0, %1}, [%2];\n\t}"
         : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred));
 }
 __device__ __forceinline__ float ldg_one(const float *p, bool pred)
@@ -56,11 +62,19 @@ __device__ __forceinline__ double ldg_one(const double *p, bool pred)
 }
 __device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
 {
+#ifdef CHEMSIM_STORE_CS
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+#else
     *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+#endif
 }
 __device__ __forceinline__ void store_vec(double *p, const double (&v)[2])
 {
+#ifdef CHEMSIM_STORE_CS
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
+#else
     *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+#endif
 }
 // V mask bytes as one 32-/16-bit word (0 when !pred)
 __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const float *)
@@ -78,7 +92,14 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
     return v;
 }
 
-constexpr int STEP_THREADS = 256;
+// Build-time tunables (defaults are the measured best; tools/variants.sh sweeps them).
+#ifndef CHEMSIM_STEP_THREADS
+#define CHEMSIM_STEP_THREADS 256
+#endif
+#ifndef CHEMSIM_STEP_MIN_BLOCKS
+#define CHEMSIM_STEP_MIN_BLOCKS 4   // <= 64 registers: 4 x 256 threads per SM (ptxas otherwise takes 88 for f64)
+#endif
+constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 
 // ---- the fused step, vector form ---------------------------------------------
 // Thread (tx, ty) of block (bx, by) updates the V = 16/sizeof(T) cells
@@ -89,7 +110,7 @@ constexpr int STEP_THREADS = 256;
 // first/last lane of a warp (or of the row) issues an extra scalar load, which
 // also implements the x edge (wrap or zero-fill).
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
-__global__ void __launch_bounds__(STEP_THREADS)
+__global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STEP_MIN_BLOCKS)
 step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 {
     constexpr int V = VecOf<T>::N;

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Builds experimental variants of the step kernel (compile-time switches) for an A/B sweep on the GPU.
+    python tools/variants.py build        (here, on CPU)
+    python tools/variants.py run          (under gpurun: bench each variant, print GLUPS)
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VARIANTS = {
+    "base": [],
+    "mb5": ["CHEMSIM_STEP_MIN_BLOCKS=5"],
+    "mb6": ["CHEMSIM_STEP_MIN_BLOCKS=6"],
+    "t128": ["CHEMSIM_STEP_THREADS=128"],
+    "t512": ["CHEMSIM_STEP_THREADS=512"],
+    "stcs": ["CHEMSIM_STORE_CS"],
+    "noalloc": ["CHEMSIM_LOAD_NOALLOC"],
+    "stcs_noalloc": ["CHEMSIM_STORE_CS", "CHEMSIM_LOAD_NOALLOC"],
+    "t128_mb10": ["CHEMSIM_STEP_THREADS=128", "CHEMSIM_STEP_MIN_BLOCKS=10"],
+}
+
+if sys.argv[1] == "build":
+    from chemsim_b200 import build
+    for name, defs in VARIANTS.items():
+        print(name, build.build_variant(name, defs))
+else:
+    for name in VARIANTS:
+        lib = os.path.join(ROOT, "chemsim_b200", f"libchemsim_lbm_{name}.so")
+        for dtype in ("f32", "f64"):
+            env = dict(os.environ, CHEMSIM_LBM_LIB=lib)
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu", "--dtype", dtype,
+                                  "--steps", "500", "--warmup", "20"], capture_output=True, text=True, env=env)
+            try:
+                d = json.loads(out.stdout.strip().splitlines()[-1])
+                print(f"{name:14s} {dtype} {d['value']:.2f} GLUPS frac {d['roofline']['frac']:.4f}", flush=True)
+            except Exception:
+                print(name, dtype, "FAILED", out.stderr[-300:], flush=True)
