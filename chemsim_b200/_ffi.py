@@ -73,6 +73,7 @@ PROTOTYPES = {
     "chemsim_lbm_get_geometry": (_I, [_H, _P, _SZ]),
     "chemsim_lbm_total_mass": (_I, [_H, C.POINTER(_D)]),
     "chemsim_lbm_total_mass_global": (_I, [_H, C.POINTER(_D)]),
+    "chemsim_lbm_render": (_I, [_H, _I, _I, _P, _SZ]),
     "chemsim_lbm_is_unstable": (_I, [_H, C.POINTER(_I)]),
     "chemsim_lbm_cuda_stream": (_I, [_H, C.POINTER(_P)]),
     "chemsim_lbm_kernel_launches": (_I, [_H, C.POINTER(C.c_uint64)]),

@@ -367,6 +367,115 @@ mask_flags_kernel(const uint8_t *mask, int mask_pitch, int W, int row_begin, int
     if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) atomicOr(any, 1);
 }
 
+// ---- device-side render.rs -----------------------------------------------------
+// The scalar a render mode normalises: render_scalar_field (src/render.rs:23-89) uses
+// the field itself, render_vector_field (:91-178) uses mag = vx*vx + vy*vy.
+template <typename T>
+__device__ __forceinline__ float render_scalar(const T (&g)[Q], int mode, float &vx, float &vy)
+{
+    vx = 0.f; vy = 0.f;
+    if (mode == RENDER_DENSITY) return (float)density(g);
+    if (mode == RENDER_MOMENTUM) {
+        T mx, my; momentum(g, mx, my);
+        vx = (float)mx; vy = (float)my;
+    } else {
+        const Moments<T> m = moments(g);
+        vx = (float)m.vx; vy = (float)m.vy;
+    }
+    const float mag = __fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy));
+    return mode == RENDER_SPEED ? __fsqrt_rn(mag) : mag;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+render_stats_partial_kernel(const T *src, size_t plane, int pitch, int W, int H, int mode, double *partials)
+{
+    double s1 = 0.0, s2 = 0.0;
+    const size_t cells = (size_t)W * H;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(c / W), x = (int)(c % W);
+        T g[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + 1) * pitch + x];
+        float vx, vy;
+        const double v = (double)render_scalar(g, mode, vx, vy);
+        s1 += v; s2 += v * v;
+    }
+    const double b1 = block_sum(s1);
+    __syncthreads();
+    const double b2 = block_sum(s2);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = b1; partials[2 * blockIdx.x + 1] = b2; }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+render_stats_final_kernel(const double *partials, int n, double cells, double *stats)
+{
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { s1 += partials[2 * i]; s2 += partials[2 * i + 1]; }
+    const double b1 = block_sum(s1);
+    __syncthreads();
+    const double b2 = block_sum(s2);
+    if (threadIdx.x == 0) {
+        const double mean = b1 / cells;
+        double var = b2 / cells - mean * mean;         // population variance (af::stdev_all)
+        if (var < 0.0) var = 0.0;
+        stats[0] = mean;
+        stats[1] = sqrt(var);
+    }
+}
+
+// af::hsv2rgb on one pixel (h, s, v in [0,1])
+__device__ __forceinline__ void hsv2rgb(float h, float s, float v, float &r, float &g, float &b)
+{
+    const float h6 = h * 6.0f;
+    const int m = (int)h6;
+    const float f = h6 - (float)m;
+    const float p = v * (1.0f - s), q = v * (1.0f - s * f), t = v * (1.0f - s * (1.0f - f));
+    switch (m) {
+    case 0: r = v; g = t; b = p; break;
+    case 1: r = q; g = v; b = p; break;
+    case 2: r = p; g = v; b = t; break;
+    case 3: r = p; g = q; b = v; break;
+    case 4: r = t; g = p; b = v; break;
+    case 5: r = v; g = p; b = q; break;
+    default: r = v; g = t; b = p; break;              // h == 1 wraps to red
+    }
+}
+
+__device__ __forceinline__ unsigned char to_u8(float c)   // (256.0 * c).round().min(255.0).max(0.0) as u8
+{
+    return (unsigned char)fmaxf(fminf(roundf(256.0f * c), 255.0f), 0.0f);
+}
+
+template <typename T>
+__global__ void render_image_kernel(const T *src, size_t plane, int pitch, int W, int H, int mode,
+                                    const double *stats, const uint8_t *mask, int mask_pitch, uchar4 *rgba)
+{
+    const int x = blockIdx.y * blockDim.x + threadIdx.x;
+    const int y = blockIdx.x;
+    if (x >= W || y >= H) return;
+    T g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + 1) * pitch + x];
+    float vx, vy;
+    const float field = render_scalar(g, mode, vx, vy);
+    const float avg = (float)stats[0], inv_std = 1.0f / (float)stats[1];      // `avg as f32`, `1.0 / std as f32`
+    const float z = (field - avg) * inv_std;
+    float val = 1.0f / (1.0f + expf(-z));                                     // Matrix::logistic = af::sigmoid
+    float hue = 0.0f, sat = 1.0f;                                             // render_scalar_field :31-37
+    if (mode == RENDER_VELOCITY || mode == RENDER_MOMENTUM) {                 // render_vector_field :116-128
+        hue = (atan2f(vy, vx) + 3.14159274f) * (0.318309886f * 0.5f);
+        sat = 0.8f;
+    }
+    hue = fminf(fmaxf(hue, 0.0f), 1.0f);                                      // .clamp(0.0, 1.0)
+    val = fminf(fmaxf(val, 0.0f), 1.0f);
+    float r, gg, b;
+    hsv2rgb(hue, sat, val, r, gg, b);
+    uchar4 px = make_uchar4(to_u8(r), to_u8(gg), to_u8(b), 255);
+    if (mask && mask[(size_t)y * mask_pitch + x]) px = make_uchar4(0, 0, 255, 255);   // render_geometry :7-21
+    rgba[(size_t)y * W + x] = px;
+}
+
 inline int check_launch()
 {
     const cudaError_t e = cudaGetLastError();
@@ -485,6 +594,28 @@ int launch_is_unstable(const T *src, size_t plane, int pitch, int W, int H, cons
     return e ? e : 1;
 }
 
+template <typename T>
+int launch_render_stats(const T *src, size_t plane, int pitch, int W, int H, int mode, double *partials,
+                        double *stats, cudaStream_t s)
+{
+    int blocks = reduction_blocks((size_t)W * H);
+    if (blocks > RED_MAX_BLOCKS / 2) blocks = RED_MAX_BLOCKS / 2;     // two doubles per block
+    render_stats_partial_kernel<T><<<blocks, RED_THREADS, 0, s>>>(src, plane, pitch, W, H, mode, partials);
+    render_stats_final_kernel<<<1, RED_THREADS, 0, s>>>(partials, blocks, (double)W * (double)H, stats);
+    const int e = check_launch();
+    return e ? e : 2;
+}
+
+template <typename T>
+int launch_render_image(const T *src, size_t plane, int pitch, int W, int H, int mode, const double *stats,
+                        const uint8_t *mask, int mask_pitch, uchar4 *rgba, cudaStream_t s)
+{
+    const dim3 block(256), grid(H, (W + 255) / 256);
+    render_image_kernel<T><<<grid, block, 0, s>>>(src, plane, pitch, W, H, mode, stats, mask, mask_pitch, rgba);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
 int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin, int rows, uint8_t *flags,
                       int flag_pitch, int *any, cudaStream_t s)
 {
@@ -502,7 +633,10 @@ int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin,
                                             const Consts<T> &, cudaStream_t);                                        \
     template int launch_readout<T>(const ReadoutArgs<T> &, cudaStream_t);                                            \
     template int launch_total_mass<T>(const T *, size_t, int, int, int, double *, double *, cudaStream_t);           \
-    template int launch_is_unstable<T>(const T *, size_t, int, int, int, const Consts<T> &, int *, cudaStream_t);
+    template int launch_is_unstable<T>(const T *, size_t, int, int, int, const Consts<T> &, int *, cudaStream_t);  \
+    template int launch_render_stats<T>(const T *, size_t, int, int, int, int, double *, double *, cudaStream_t);    \
+    template int launch_render_image<T>(const T *, size_t, int, int, int, int, const double *, const uint8_t *, int, \
+                                        uchar4 *, cudaStream_t);
 
 CHEMSIM_INSTANTIATE(float)
 CHEMSIM_INSTANTIATE(double)

@@ -60,6 +60,17 @@ template <typename T> int launch_init_equilibrium(const T *rho, const T *vx, con
 template <typename T> int launch_readout(const ReadoutArgs<T> &a, cudaStream_t s);
 // partials: at least mass_partials_capacity() doubles; out: one double
 int mass_partials_capacity();
+
+// Device-side render.rs: RGBA8 image of a macroscopic field.
+enum RenderMode : int { RENDER_DENSITY = 0, RENDER_SPEED = 1, RENDER_VELOCITY = 2, RENDER_MOMENTUM = 3 };
+// pass 1: stats[0] = mean, stats[1] = population standard deviation of the displayed scalar
+// (the field itself for DENSITY/SPEED, vx^2+vy^2 for the vector modes); partials: 2*capacity doubles
+template <typename T> int launch_render_stats(const T *src, size_t plane, int pitch, int W, int H, int mode,
+                                              double *partials, double *stats, cudaStream_t s);
+// pass 2: colour mapping (z-score -> logistic -> HSV -> RGB) + geometry overlay -> rgba[y*W+x]
+template <typename T> int launch_render_image(const T *src, size_t plane, int pitch, int W, int H, int mode,
+                                              const double *stats, const uint8_t *mask, int mask_pitch,
+                                              uchar4 *rgba, cudaStream_t s);
 template <typename T> int launch_total_mass(const T *src, size_t plane, int pitch, int W, int H, double *partials,
                                             double *out, cudaStream_t s);
 template <typename T> int launch_is_unstable(const T *src, size_t plane, int pitch, int W, int H, const Consts<T> &k,

@@ -922,6 +922,35 @@ int chemsim_lbm_total_mass_global(chemsim_lbm_t *h, double *out)
     return CHEMSIM_LBM_OK;
 }
 
+int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t *rgba, size_t n_pixels)
+{
+    if (!h || !rgba) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode < RENDER_DENSITY || mode > RENDER_MOMENTUM) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "unknown render mode");
+    BIND(h);
+    const int c = check_n(h, n_pixels);
+    if (c) return c;
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    if (h->nranks > 1) return fail(h, CHEMSIM_LBM_ERR_UNSUPPORTED, "render needs the whole lattice on one GPU (mean/stdev are global)");
+    const size_t bytes = n_pixels * 4;
+    const int rs = ensure_stage(h, 1, bytes);
+    if (rs) return rs;
+    const uint8_t *mask = overlay_geometry ? h->mask : nullptr;
+    if (h->dtype == CHEMSIM_LBM_F32) {
+        LAUNCH_TRY(h, launch_render_stats<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
+                                                 h->d_partials, h->d_scalar, h->stream));
+        LAUNCH_TRY(h, launch_render_image<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
+                                                 h->d_scalar, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
+    } else {
+        LAUNCH_TRY(h, launch_render_stats<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
+                                                  h->d_partials, h->d_scalar, h->stream));
+        LAUNCH_TRY(h, launch_render_image<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
+                                                  h->d_scalar, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(rgba, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CHEMSIM_LBM_OK;
+}
+
 int chemsim_lbm_is_unstable(chemsim_lbm_t *h, int *out)
 {
     if (!h || !out) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");

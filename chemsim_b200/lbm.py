@@ -415,6 +415,16 @@ class State:
         dirs = D2Q9.directions()
         return [(dirs[q], self._get1(self._lib.chemsim_lbm_get_non_equilibrium, q)) for q in range(9)]
 
+    RENDER_DENSITY, RENDER_SPEED, RENDER_VELOCITY, RENDER_MOMENTUM = range(4)
+
+    def render(self, mode: int = 0, overlay_geometry: bool = True) -> np.ndarray:
+        """render_scalar_field / render_vector_field + render_geometry (src/render.rs) on the
+        device: (h, w, 4) uint8 RGBA image."""
+        out = np.empty((self.local_height, self.width, 4), dtype=np.uint8)
+        self._check(self._lib.chemsim_lbm_render(self._h, mode, int(overlay_geometry),
+                                                 out.ctypes.data_as(C.c_void_p), self._n))
+        return out
+
     def is_unstable(self) -> bool:
         out = C.c_int()
         self._check(self._lib.chemsim_lbm_is_unstable(self._h, C.byref(out)))

@@ -213,6 +213,15 @@ int chemsim_lbm_get_geometry(chemsim_lbm_t *h, uint8_t *dst, size_t n);         
 int chemsim_lbm_total_mass(chemsim_lbm_t *h, double *out);
 int chemsim_lbm_total_mass_global(chemsim_lbm_t *h, double *out);
 
+/* render.rs evaluated on the device: one RGBA8 image instead of 1-3 float
+ * planes per frame.  mode 0/1 = render_scalar_field(&state.density() / &state.speed())
+ * (src/render.rs:23-89), mode 2/3 = render_vector_field(&state.velocity() /
+ * &state.momentum_density()) (:91-178): z-score with af::mean_all / af::stdev_all (population
+ * standard deviation), logistic, HSV -> RGB, `(256*c).round().min(255).max(0) as u8`; with
+ * overlay_geometry != 0 solid cells become RGB(0,0,255) as render_geometry does (:7-21).
+ * rgba: n_pixels = width*height pixels of 4 bytes, row-major y*w+x, alpha 255 (display.rs:41-43). */
+int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t *rgba, size_t n_pixels);
+
 /* State::is_unstable (src/lbm.rs:815-818): min(f_eq,0) < 0 on this handle's cells. */
 int chemsim_lbm_is_unstable(chemsim_lbm_t *h, int *out);
 
