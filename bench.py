@@ -239,6 +239,8 @@ def run_gpu_arm(args):
     w, hg, scaling = workload_shape(args.workload, world)
     state = lbm.State.create((w, hg), lbm.BGK(TAU), lbm.Discretization(1.0, 1.0), dtype=dtype,
                              edge=lbm.EDGE_PERIODIC, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+    if args.halo == "p2p" and world > 1:
+        state.enable_p2p_halo()
     hl, y0 = state.local_height, state.row_offset
     # initialise in row chunks so that host memory stays bounded for the 32768^2 / 16384^2 workloads
     chunk = 2048
@@ -314,6 +316,7 @@ def run_gpu_arm(args):
             "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": args.workload, "lattice": f"{w}x{hg}", "per_gpu": f"{w}x{hl}",
                        "collision": "BGK tau=0.8", "edge": "periodic", "sharding": f"y-slabs x{world}",
+                       "halo": state.halo_mode() if world > 1 else "none",
                        "l2": "working set %.2f GiB per GPU >> 126 MB L2 (no flush needed)" % (2 * 9 * w * hl * (bpc / 18) / 2**30),
                        "kernel": state.step_kernel_name(),
                        "mass_drift_rel": abs(mass1 - mass0) / mass0},
@@ -349,6 +352,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "strong", "weak16k"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
+                    help="multi-GPU halo: NCCL send/recv (default) or the fused peer-memory face kernel")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

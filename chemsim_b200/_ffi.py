@@ -43,6 +43,8 @@ PROTOTYPES = {
     "chemsim_lbm_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_H)]),
     "chemsim_lbm_create_slab": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, C.POINTER(_H)]),
     "chemsim_lbm_nccl_unique_id": (_I, [_P]),
+    "chemsim_lbm_enable_p2p_halo": (_I, [_H]),
+    "chemsim_lbm_halo_mode": (_I, [_H, C.POINTER(_I)]),
     "chemsim_lbm_destroy": (_I, [_H]),
     "chemsim_lbm_shape": (_I, [_H, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "chemsim_lbm_set_discretization": (_I, [_H, _D, _D]),

@@ -28,36 +28,52 @@ template <> struct VecOf<double> { using type = double2; static constexpr int N 
 #define CHEMSIM_LD_HINT ""
 #endif
 
-// Predicated, branch-free global loads through the read-only path.  The source
-// buffer is never written by the kernel that reads it (A-B buffering), so .nc is
-// legal.  Predication instead of `if` keeps every load of a thread in ONE
-// straight-line batch: all of them are in flight before the first use.
+// Predicated, branch-free global loads.  NC=true takes the read-only path: the
+// source buffer is never written by the kernel that reads it (A-B buffering), so
+// .nc is legal.  NC=false (coherent) is used by the P2P face kernel, whose ghost
+// rows are written by the neighbouring GPU while the kernel may already be resident.
+// Predication instead of `if` keeps every load of a thread in ONE straight-line
+// batch: all of them are in flight before the first use.
+#define CHEMSIM_LDG_BODY(NCSTR)                                                                       \
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"                                             \
+        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"                    \
+        "@q ld.global" NCSTR ".v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"                                   \
+        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred))
+template <bool NC>
 __device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4])
 {
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
-        "@q ld.global.nc" CHEMSIM_LD_HINT ".v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred));
+    if (NC) CHEMSIM_LDG_BODY(".nc" CHEMSIM_LD_HINT); else CHEMSIM_LDG_BODY("");
 }
+#undef CHEMSIM_LDG_BODY
+#define CHEMSIM_LDG_BODY(NCSTR)                                                                       \
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"                                             \
+        "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"                                                        \
+        "@q ld.global" NCSTR ".v2.f64 {%0, %1}, [%2];\n\t}"                                           \
+        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred))
+template <bool NC>
 __device__ __forceinline__ void ldg_vec(const double *p, bool pred, double (&v)[2])
 {
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
-        "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"
-        "@q ld.global.nc" CHEMSIM_LD_HINT ".v2.f64 {%0, %1}, [%2];\n\t}"
-        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred));
+    if (NC) CHEMSIM_LDG_BODY(".nc" CHEMSIM_LD_HINT); else CHEMSIM_LDG_BODY("");
 }
+#undef CHEMSIM_LDG_BODY
+template <bool NC>
 __device__ __forceinline__ float ldg_one(const float *p, bool pred)
 {
     float v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
-        : "=&f"(v) : "l"(p), "r"((int)pred));
+    if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+                : "=&f"(v) : "l"(p), "r"((int)pred));
+    else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.f32 %0, [%1];\n\t}"
+                : "=&f"(v) : "l"(p), "r"((int)pred));
     return v;
 }
+template <bool NC>
 __device__ __forceinline__ double ldg_one(const double *p, bool pred)
 {
     double v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
-        : "=&d"(v) : "l"(p), "r"((int)pred));
+    if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
+                : "=&d"(v) : "l"(p), "r"((int)pred));
+    else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.f64 %0, [%1];\n\t}"
+                : "=&d"(v) : "l"(p), "r"((int)pred));
     return v;
 }
 __device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
@@ -109,18 +125,14 @@ constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 // aligned vector plus ONE element shuffled in from the adjacent lane; only the
 // first/last lane of a warp (or of the row) issues an extra scalar load, which
 // also implements the x edge (wrap or zero-fill).
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
-__global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STEP_MIN_BLOCKS)
-step_vec_kernel(const __grid_constant__ StepArgs<T> a)
+// The update of V cells of row y by one thread (see the kernel comment above).
+// P2P=true additionally stores the populations that leave the slab through this face
+// row straight into the neighbouring GPU's ghost row (peer-mapped memory, NVLink).
+template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool P2P>
+__device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y, const int xv, const int lane)
 {
     constexpr int V = VecOf<T>::N;
-    // MULTIROW=false: one row per block (blockDim.y == 1), so the row index and all
-    // nine source-row addresses are block-uniform and live in uniform registers.
-    const int yi = MULTIROW ? blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
-    if (yi >= a.y_count) return;                     // warp-uniform
-    const int y = a.y_begin + yi * a.y_stride;
-    const int lane = threadIdx.x & 31;
-    const int xv = blockIdx.y * blockDim.x + threadIdx.x;
+    constexpr bool NC = !P2P;
     const int nvec = a.W / V;
     if (xv - lane >= nvec) return;                   // whole warp beyond the row
     const bool active = xv < nvec;
@@ -146,9 +158,9 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
         int sy = y - ey_of(q);
         if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
         const T *row = a.src + (size_t)q * a.plane + (size_t)(sy + 1) * a.pitch;
-        ldg_vec(row + x0, active, v[q]);
-        if (ex_of(q) == 1)       e[q] = ldg_one(row + left_x, need_left);
-        else if (ex_of(q) == -1) e[q] = ldg_one(row + right_x, need_right);
+        ldg_vec<NC>(row + x0, active, v[q]);
+        if (ex_of(q) == 1)       e[q] = ldg_one<NC>(row + left_x, need_left);
+        else if (ex_of(q) == -1) e[q] = ldg_one<NC>(row + right_x, need_right);
         else                     e[q] = T(0);
     }
     unsigned maskw = 0;
@@ -192,6 +204,82 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
     T *out = a.dst + (size_t)(y + 1) * a.pitch + x0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) store_vec(out + (size_t)q * a.plane, g[q]);
+
+    // ---- phase 5 (P2P face rows): the halo, written where the neighbour reads it --
+    if (P2P) {
+        const HaloP2P &p = a.halo;
+        if (y == a.H - 1 && p.down_dst) {            // dy=+1 movers -> lower neighbour's ghost row −1 (plane row 0)
+            T *peer = (T *)p.down_dst + x0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) if (ey_of(q) == 1) store_vec(peer + (size_t)q * p.down_plane, g[q]);
+        }
+        if (y == 0 && p.up_dst) {                    // dy=−1 movers -> upper neighbour's ghost row H_up
+            T *peer = (T *)p.up_dst + (size_t)p.up_ghost_row * a.pitch + x0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) if (ey_of(q) == -1) store_vec(peer + (size_t)q * p.up_plane, g[q]);
+        }
+    }
+}
+
+template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
+__global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STEP_MIN_BLOCKS)
+step_vec_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    // MULTIROW=false: one row per block (blockDim.y == 1), so the row index and all
+    // nine source-row addresses are block-uniform and live in uniform registers.
+    const int yi = MULTIROW ? blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
+    if (yi >= a.y_count) return;                     // warp-uniform
+    step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, a.y_begin + yi * a.y_stride,
+                                                       blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31);
+}
+
+// ---- fused face update + halo exchange over peer memory ------------------------
+// One launch updates the two face rows {0, H−1} of a slab and delivers the
+// populations that cross each face into the neighbouring GPUs' ghost rows with plain
+// stores through NVLink-mapped pointers (cudaIpc): compute and exchange are ONE kernel,
+// there is no pack buffer and no separate communication kernel.
+// Flow control is a step counter per face in each GPU's memory:
+//   wait   : ghost rows of step t are valid once the neighbour published flag >= t
+//   signal : after every block has stored (and fenced) its rows, the last block to
+//            finish publishes t+1 into both neighbours' flags
+// A-B buffering makes one step of slack enough: a neighbour that is one step ahead
+// writes into the buffer this GPU is not reading.
+__device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned want, int *error)
+{
+    if (!flag) return;
+    unsigned spins = 0;
+    while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - want) < 0) {
+        __nanosleep(128);
+        if (++spins > (1u << 27)) { atomicExch(error, 1); break; }   // ~20 s: report instead of hanging
+    }
+    __threadfence_system();
+}
+
+template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+step_face_p2p_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    const HaloP2P &p = a.halo;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        wait_flag(p.wait_up, p.step, p.error);
+        wait_flag(p.wait_down, p.step, p.error);
+    }
+    __syncthreads();
+    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
+    if (yi < a.y_count)
+        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, a.y_begin + yi * a.y_stride,
+                                                          blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31);
+    __threadfence_system();                          // my stores (local and peer) are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(p.done, 1u) == total - 1) {    // ... before the last block publishes the step
+            *p.done = 0;
+            __threadfence_system();
+            if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
+            if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
+        }
+    }
 }
 
 // ---- the fused step, one cell per thread (any width) -------------------------
@@ -537,6 +625,44 @@ void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
     }
 }
 
+template <typename T, int COL>
+void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s)
+{
+    constexpr int V = VecOf<T>::N;
+    const int rows = a.y_count, nvec = a.W / V;
+    int bx = ((nvec + 31) / 32) * 32;
+    if (bx > STEP_THREADS) bx = STEP_THREADS;
+    int by = STEP_THREADS / bx;
+    if (by > rows) by = rows;
+    const dim3 block(bx, by);
+    const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
+    if (a.periodic_x) {
+        if (a.has_mask) step_face_p2p_kernel<T, true, true, COL><<<grid, block, 0, s>>>(a);
+        else            step_face_p2p_kernel<T, true, false, COL><<<grid, block, 0, s>>>(a);
+    } else {
+        if (a.has_mask) step_face_p2p_kernel<T, false, true, COL><<<grid, block, 0, s>>>(a);
+        else            step_face_p2p_kernel<T, false, false, COL><<<grid, block, 0, s>>>(a);
+    }
+}
+
+template <typename T>
+bool face_p2p_supported(const StepArgs<T> &a) { return use_vec(a); }
+
+template <typename T>
+int launch_face_p2p(const StepArgs<T> &a, cudaStream_t s)
+{
+    if (a.y_count <= 0 || !use_vec(a)) return -(int)cudaErrorInvalidValue;
+    switch (a.collision) {
+    case COL_BGK:         launch_face_p2p_col<T, COL_BGK>(a, s); break;
+    case COL_TRT:         launch_face_p2p_col<T, COL_TRT>(a, s); break;
+    case COL_REGULARIZED: launch_face_p2p_col<T, COL_REGULARIZED>(a, s); break;
+    case COL_KBC:         launch_face_p2p_col<T, COL_KBC>(a, s); break;
+    default: return -(int)cudaErrorInvalidValue;
+    }
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
 template <typename T>
 int launch_step(const StepArgs<T> &a, cudaStream_t s)
 {
@@ -628,6 +754,8 @@ int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin,
 
 #define CHEMSIM_INSTANTIATE(T)                                                                                       \
     template int launch_step<T>(const StepArgs<T> &, cudaStream_t);                                                  \
+    template int launch_face_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \
+    template bool face_p2p_supported<T>(const StepArgs<T> &);                                                        \
     template const char *step_kernel_name<T>(const StepArgs<T> &);                                                   \
     template int launch_init_equilibrium<T>(const T *, const T *, const T *, T *, size_t, int, int, int, int,        \
                                             const Consts<T> &, cudaStream_t);                                        \

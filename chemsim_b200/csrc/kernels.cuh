@@ -11,6 +11,18 @@ namespace chemsim {
 //   rows) and column x lives at  base[q*plane + (y+1)*pitch + x].
 // pitch is W rounded up to 128 bytes so every row starts on a cache line and
 // 128-bit vector accesses at x % VEC == 0 are aligned.
+// Peer-memory halo of a y-slab (filled in only for the P2P face kernel).
+struct HaloP2P {
+    void *up_dst = nullptr, *down_dst = nullptr;   // the neighbours' destination population buffers (peer-mapped)
+    size_t up_plane = 0, down_plane = 0;           // their plane strides, in elements
+    int up_ghost_row = 0;                          // plane row of the upper neighbour's ghost row H (= H_up + 1)
+    const unsigned *wait_up = nullptr, *wait_down = nullptr;   // local step flags the neighbours publish into
+    unsigned *signal_up = nullptr, *signal_down = nullptr;     // the neighbours' flags this GPU publishes into
+    unsigned *done = nullptr;                      // local counter of finished blocks
+    unsigned step = 0;                             // t: needs flags >= t, publishes t+1
+    int *error = nullptr;                          // set to 1 if a wait timed out
+};
+
 template <typename T>
 struct StepArgs {
     const T *src;
@@ -29,6 +41,7 @@ struct StepArgs {
     const uint8_t *mask_flags;  // per row, one byte per 64-cell segment: any solid cell in it?
     int flag_pitch;             // (a warp of the vector kernel covers whole segments and skips
                                 //  the mask load when they are solid-free)
+    HaloP2P halo;
     Consts<T> k;
 };
 
@@ -53,6 +66,9 @@ struct ReadoutArgs {
 // launch counter) or a negative cudaError_t.
 template <typename T> int launch_step(const StepArgs<T> &a, cudaStream_t s);
 template <typename T> const char *step_kernel_name(const StepArgs<T> &a);
+// the two face rows + the halo stores into the neighbours' ghost rows, one kernel (vector widths only)
+template <typename T> int launch_face_p2p(const StepArgs<T> &a, cudaStream_t s);
+template <typename T> bool face_p2p_supported(const StepArgs<T> &a);
 // rows [row_begin, row_begin + rows) of the lattice from dense (pitch == W) fields of `rows` rows
 template <typename T> int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane,
                                                   int pitch, int W, int row_begin, int rows, const Consts<T> &k,

@@ -108,6 +108,15 @@ struct chemsim_lbm {
     cudaEvent_t ev_face = nullptr, ev_interior = nullptr, ev_halo = nullptr;
     ncclComm_t comm = nullptr;
     bool ghosts_valid = false;
+    // peer-memory halo (chemsim_lbm_enable_p2p_halo): the face kernel stores into the
+    // neighbours' ghost rows directly; NCCL is then only used for the first exchange
+    int halo_mode = CHEMSIM_LBM_HALO_NCCL;
+    unsigned step_index = 0;                        // steps taken since creation (same on every rank)
+    unsigned *p2p_flags = nullptr;                  // [0] from_up, [1] from_down, [2] done counter, [3] error
+    void *peer_up_buf[2] = {nullptr, nullptr}, *peer_down_buf[2] = {nullptr, nullptr};
+    unsigned *peer_up_flags = nullptr, *peer_down_flags = nullptr;
+    int peer_up_H = 0, peer_down_H = 0;
+    bool peer_same = false;                         // both neighbours are the same rank (nranks == 2)
     bool have_populations = false;
 
     float time_f = 0.f;
@@ -241,6 +250,136 @@ int exchange(chemsim_lbm *h, int b)
     return 0;
 }
 
+// Arguments of the P2P face kernel for the step that writes buffer cur^1.
+void fill_halo(const chemsim_lbm *h, HaloP2P &p)
+{
+    const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
+    const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
+    const int b = h->cur ^ 1;
+    p = HaloP2P();
+    if (has_up) {
+        p.up_dst = h->peer_up_buf[b];
+        p.up_plane = (size_t)(h->peer_up_H + 2) * h->pitch;
+        p.up_ghost_row = h->peer_up_H + 1;
+        p.wait_up = h->p2p_flags + 0;
+        p.signal_up = h->peer_up_flags + 1;          // I am the upper neighbour's lower neighbour
+    }
+    if (has_down) {
+        p.down_dst = h->peer_down_buf[b];
+        p.down_plane = (size_t)(h->peer_down_H + 2) * h->pitch;
+        p.wait_down = h->p2p_flags + 1;
+        p.signal_down = h->peer_down_flags + 0;      // I am the lower neighbour's upper neighbour
+    }
+    p.done = h->p2p_flags + 2;
+    p.error = (int *)(h->p2p_flags + 3);
+    p.step = h->step_index;
+}
+
+struct P2PInfo {                 // what the ranks tell each other (all-gathered over NCCL)
+    cudaIpcMemHandle_t buf[2];
+    cudaIpcMemHandle_t flags;
+    int H;
+    int ok;
+    char pad[256 - 3 * sizeof(cudaIpcMemHandle_t) - 2 * sizeof(int)];
+};
+static_assert(sizeof(P2PInfo) == 256, "P2PInfo layout");
+
+void close_p2p(chemsim_lbm *h)
+{
+    for (int b = 0; b < 2; ++b) {
+        if (h->peer_up_buf[b]) cudaIpcCloseMemHandle(h->peer_up_buf[b]);
+        if (h->peer_down_buf[b] && !h->peer_same) cudaIpcCloseMemHandle(h->peer_down_buf[b]);
+        h->peer_up_buf[b] = h->peer_down_buf[b] = nullptr;
+    }
+    if (h->peer_up_flags) cudaIpcCloseMemHandle(h->peer_up_flags);
+    if (h->peer_down_flags && !h->peer_same) cudaIpcCloseMemHandle(h->peer_down_flags);
+    h->peer_up_flags = h->peer_down_flags = nullptr;
+}
+
+// Collective over all ranks of the lattice.  Every rank ends in the same mode.
+int enable_p2p(chemsim_lbm *h)
+{
+    if (h->nranks == 1 || h->halo_mode == CHEMSIM_LBM_HALO_P2P) return 0;
+    const NcclDyn &n = nccl_dyn();
+    const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
+    const int up = (h->rank + h->nranks - 1) % h->nranks, down = (h->rank + 1) % h->nranks;
+    const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
+    h->peer_same = has_up && has_down && up == down;
+
+    P2PInfo mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.H = h->H;
+    mine.ok = 1;
+    if (!h->p2p_flags) {
+        if (cudaMalloc((void **)&h->p2p_flags, 4 * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
+        else if (cudaMemset(h->p2p_flags, 0, 4 * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
+    }
+    const bool vec_ok = h->dtype == CHEMSIM_LBM_F32 ? face_p2p_supported(step_args<float>(h, 0, 1))
+                                                    : face_p2p_supported(step_args<double>(h, 0, 1));
+    if (!vec_ok) mine.ok = 0;                       // ragged widths keep the NCCL exchange
+    if (mine.ok && (cudaIpcGetMemHandle(&mine.buf[0], h->buf[0]) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&mine.buf[1], h->buf[1]) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&mine.flags, h->p2p_flags) != cudaSuccess)) {
+        mine.ok = 0;
+        cudaGetLastError();
+    }
+    // all-gather the handles
+    char *d_all = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&d_all, sizeof(P2PInfo) * (h->nranks + 1)));
+    CUDA_TRY(h, cudaMemcpyAsync(d_all + sizeof(P2PInfo) * h->nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    NCCL_TRY(h, n.AllGather(d_all + sizeof(P2PInfo) * h->nranks, d_all, sizeof(P2PInfo), ncclChar, h->comm, h->stream));
+    std::string all(sizeof(P2PInfo) * h->nranks, '\0');
+    CUDA_TRY(h, cudaMemcpyAsync(&all[0], d_all, all.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const P2PInfo *info = reinterpret_cast<const P2PInfo *>(all.data());
+    int ok = 1;
+    for (int r = 0; r < h->nranks; ++r) ok &= info[r].ok;
+    // map the neighbours' buffers
+    if (ok) {
+        const unsigned fl = cudaIpcMemLazyEnablePeerAccess;
+        if (has_up) {
+            h->peer_up_H = info[up].H;
+            for (int b = 0; b < 2 && ok; ++b)
+                if (cudaIpcOpenMemHandle(&h->peer_up_buf[b], info[up].buf[b], fl) != cudaSuccess) ok = 0;
+            if (ok && cudaIpcOpenMemHandle((void **)&h->peer_up_flags, info[up].flags, fl) != cudaSuccess) ok = 0;
+        }
+        if (has_down && ok) {
+            h->peer_down_H = info[down].H;
+            if (h->peer_same) {
+                h->peer_down_buf[0] = h->peer_up_buf[0]; h->peer_down_buf[1] = h->peer_up_buf[1];
+                h->peer_down_flags = h->peer_up_flags;
+            } else {
+                for (int b = 0; b < 2 && ok; ++b)
+                    if (cudaIpcOpenMemHandle(&h->peer_down_buf[b], info[down].buf[b], fl) != cudaSuccess) ok = 0;
+                if (ok && cudaIpcOpenMemHandle((void **)&h->peer_down_flags, info[down].flags, fl) != cudaSuccess) ok = 0;
+            }
+        }
+        if (!ok) cudaGetLastError();
+    }
+    // agree: P2P only if every rank mapped its neighbours
+    int *d_ok = reinterpret_cast<int *>(d_all);
+    CUDA_TRY(h, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NCCL_TRY(h, n.AllReduce(d_ok, d_ok + 1, 1, ncclInt, ncclMin, h->comm, h->stream));
+    int all_ok = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&all_ok, d_ok + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaFree(d_all));
+    if (all_ok) {
+        // flags restart from the current step on every rank: the first P2P step reads ghost
+        // rows that the NCCL exchange of begin_sharded() delivers
+        const unsigned init[4] = {h->step_index, h->step_index, 0u, 0u};
+        CUDA_TRY(h, cudaMemcpy(h->p2p_flags, init, sizeof(init), cudaMemcpyHostToDevice));
+        h->ghosts_valid = false;
+        h->halo_mode = CHEMSIM_LBM_HALO_P2P;
+        // nobody may publish into my flags before they are initialised
+        NCCL_TRY(h, n.AllReduce(h->d_scalar, h->d_scalar + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else {
+        close_p2p(h);
+    }
+    return 0;
+}
+
 // Sharded stepping runs on two streams:
 //   stream      (normal priority)  interior rows 1 … H−2, which read no ghost row
 //   comm_stream (highest priority) the two face rows, then the NCCL exchange of them
@@ -276,6 +415,7 @@ int step_impl(chemsim_lbm *h, int nsteps)
         for (int s = 0; s < nsteps; ++s) {
             LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H), h->stream));
             h->cur ^= 1;
+            h->step_index += 1;
         }
         return 0;
     }
@@ -286,14 +426,23 @@ int step_impl(chemsim_lbm *h, int nsteps)
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_face, 0));
         CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_interior, 0));
         // halo stream: face rows {0, H−1} of step s, then ship them
-        LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H > 1 ? 2 : 1, h->H > 1 ? h->H - 1 : 1), h->comm_stream));
-        CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
-        const int r = exchange(h, h->cur ^ 1);
-        if (r) return r;
+        StepArgs<T> face = step_args<T>(h, 0, h->H > 1 ? 2 : 1, h->H > 1 ? h->H - 1 : 1);
+        if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
+            // ONE kernel: face rows + stores into the neighbours' ghost rows + step flags
+            fill_halo(h, face.halo);
+            LAUNCH_TRY(h, launch_face_p2p<T>(face, h->comm_stream));
+            CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
+        } else {
+            LAUNCH_TRY(h, launch_step<T>(face, h->comm_stream));
+            CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
+            const int r = exchange(h, h->cur ^ 1);
+            if (r) return r;
+        }
         // main stream: interior of step s
         if (h->H > 2) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 1, h->H - 2), h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_interior, h->stream));
         h->cur ^= 1;
+        h->step_index += 1;
     }
     // later work on the main stream (readouts, uploads) sees the finished halo work
     CUDA_TRY(h, cudaEventRecord(h->ev_halo, h->comm_stream));
@@ -572,12 +721,35 @@ int chemsim_lbm_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *
     return CHEMSIM_LBM_OK;
 }
 
+int chemsim_lbm_enable_p2p_halo(chemsim_lbm_t *h)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    BIND(h);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
+    return enable_p2p(h);
+}
+
+int chemsim_lbm_halo_mode(const chemsim_lbm_t *h, int *mode)
+{
+    if (!h || !mode) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *mode = h->halo_mode;
+    return CHEMSIM_LBM_OK;
+}
+
 int chemsim_lbm_destroy(chemsim_lbm_t *h)
 {
     if (!h) return CHEMSIM_LBM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P && h->comm) {
+        // neighbours may still be storing into my ghost rows: wait for everyone before unmapping
+        nccl_dyn().AllReduce(h->d_scalar, h->d_scalar + 1, 1, ncclDouble, ncclSum, h->comm, h->stream);
+        cudaStreamSynchronize(h->stream);
+        close_p2p(h);
+    }
+    if (h->p2p_flags) cudaFree(h->p2p_flags);
     if (h->comm) nccl_dyn().CommDestroy(h->comm);
     for (int b = 0; b < 2; ++b) if (h->buf[b]) cudaFree(h->buf[b]);
     if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
@@ -820,6 +992,11 @@ int chemsim_lbm_synchronize(chemsim_lbm_t *h)
     CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->h2d_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
+        int err = 0;
+        CUDA_TRY(h, cudaMemcpy(&err, h->p2p_flags + 3, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(h, CHEMSIM_LBM_ERR_CUDA, "peer-memory halo: a neighbour did not publish its face rows in time");
+    }
     return CHEMSIM_LBM_OK;
 }
 

@@ -24,6 +24,7 @@ struct NcclDyn {
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
 
     NcclDyn()
@@ -42,6 +43,7 @@ struct NcclDyn {
         CHEMSIM_NCCL_SYM(Send)
         CHEMSIM_NCCL_SYM(Recv)
         CHEMSIM_NCCL_SYM(AllReduce)
+        CHEMSIM_NCCL_SYM(AllGather)
         CHEMSIM_NCCL_SYM(GetErrorString)
 #undef CHEMSIM_NCCL_SYM
         ok = true;

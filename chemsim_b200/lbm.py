@@ -436,6 +436,16 @@ class State:
         self._check(fn(self._h, C.byref(out)))
         return out.value
 
+    def enable_p2p_halo(self) -> bool:
+        """Collective: switch to the fused peer-memory halo; True if every rank could."""
+        self._check(self._lib.chemsim_lbm_enable_p2p_halo(self._h))
+        return self.halo_mode() == "p2p"
+
+    def halo_mode(self) -> str:
+        out = C.c_int()
+        self._check(self._lib.chemsim_lbm_halo_mode(self._h, C.byref(out)))
+        return "p2p" if out.value == 1 else "nccl"
+
     # ---- introspection ----------------------------------------------------------
     def cuda_stream(self) -> int:
         out = C.c_void_p()

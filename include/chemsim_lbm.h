@@ -98,6 +98,17 @@ int chemsim_lbm_create_slab(int width, int global_height, int dtype, int edge, i
                             int nranks, const void *nccl_id, chemsim_lbm_t **out);
 int chemsim_lbm_nccl_unique_id(void *out_id /* CHEMSIM_LBM_NCCL_ID_BYTES */);
 
+/* Switch a sharded lattice from the NCCL exchange to the fused peer-memory halo: the
+ * face-row kernel stores the populations that cross a slab face straight into the
+ * neighbouring GPU's ghost row through a cudaIpc-mapped pointer (NVLink) and publishes a
+ * step counter the neighbour waits on — compute and exchange are one kernel, NCCL is only
+ * used for the first exchange after an upload.  COLLECTIVE: every rank of the lattice must
+ * call it at the same point.  If any rank cannot map its neighbours (no peer access, ragged
+ * width) all ranks stay in NCCL mode; chemsim_lbm_halo_mode reports the outcome. */
+typedef enum { CHEMSIM_LBM_HALO_NCCL = 0, CHEMSIM_LBM_HALO_P2P = 1 } chemsim_lbm_halo;
+int chemsim_lbm_enable_p2p_halo(chemsim_lbm_t *h);
+int chemsim_lbm_halo_mode(const chemsim_lbm_t *h, int *mode);
+
 /* Host-only helpers that expose the sharding logic (no GPU needed; the CPU tests
  * drive a gloo emulation of the exchange with them).
  * slab_rows: the rows rank `rank` owns.  halo_plan: the messages one rank issues

@@ -28,6 +28,10 @@ def main():
     dist.broadcast(ident, 0)
     state = lbm.State.create((w, hg), lbm.BGK(0.8), dtype=dtype, edge=edge, device=local, rank=rank, nranks=world,
                              nccl_id=ident.cpu().numpy().tobytes())
+    halo = sys.argv[6] if len(sys.argv) > 6 else "nccl"
+    if halo == "p2p":
+        assert state.enable_p2p_halo(), "peer-memory halo could not be enabled on this box"
+    assert state.halo_mode() == halo
     r0, h = state.row_offset, state.local_height
     assert (r0, h) == lbm.slab_rows(hg, rank, world)
     rho, vx, vy, solid = scenarios.random_state(w, hg, dtype, seed=23)
@@ -39,6 +43,7 @@ def main():
     for n in (1, 2, steps - 3):
         state.step(n)
         done += n
+    state.synchronize()          # also reports a halo time-out
     mine = state.populations_array()
     mass = state.total_mass(global_=True)
     gathered = [None] * world
@@ -54,10 +59,11 @@ def main():
         single.init_equilibrium(rho, vx, vy)
         single.geometry = solid
         single.step(steps)
+        single.synchronize()
         ok = ok and bool((single.populations_array().view(u) == got.view(u)).all())
         ok = ok and abs(mass - O.total_mass(ref)) <= 1e-12 * abs(mass)
         ok = ok and abs(m0 - O.total_mass(f0)) <= 1e-12 * abs(m0)
-        print(("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH") + f" world={world} {w}x{hg} edge={edge} {dtype_name}", flush=True)
+        print(("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH") + f" world={world} {w}x{hg} edge={edge} {dtype_name} halo={halo}", flush=True)
     state.close()
     dist.barrier()
     dist.destroy_process_group()
