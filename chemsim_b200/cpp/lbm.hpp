@@ -14,8 +14,9 @@
 //   Discretization (:75-86)             Discretization
 //   Direction, D2Q9 (:90-95, :180-323)  Direction, D2Q9
 //   compute_equilibrium (:43-71)        compute_equilibrium
-//   BGK (:345-370)                      BGK
+//   BGK / TRT / KBC / Regularized<C>    BGK, TRT, KBC, Regularized<C>            (:345-666)
 //   State<D2Q9> (:670-819)              State
+//   render_* (render.rs:7-178)          State::render (device-side)
 #pragma once
 
 #include <cmath>
@@ -89,6 +90,8 @@ struct Direction {        // src/lbm.rs:90-95
     int stencil[9];
 };
 
+// CollisionOperator impls (src/lbm.rs:327-666).  Each knows how to select itself on a
+// handle (`apply`) and reports its viscosities in Scalar like the reference.
 struct BGK {              // src/lbm.rs:345-370
     Scalar tau;
     Scalar kinematic_shear_viscosity(const Discretization &d) const
@@ -96,6 +99,40 @@ struct BGK {              // src/lbm.rs:345-370
         return (d.delta_x * d.delta_x / (3.0f * d.delta_t * d.delta_t)) * (tau - d.delta_t / 2.0f);
     }
     Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
+    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_bgk(h, tau); }
+};
+
+struct TRT {              // src/lbm.rs:374-451
+    Scalar tau_minus, tau_plus;
+    static TRT make(Scalar lambda, Scalar ks_viscosity, const Discretization &d)   // TRT::new, :380-390
+    {
+        const Scalar dt = d.delta_t, cs = d.isothermal_speed_of_sound();
+        const Scalar tau_plus = dt * ((ks_viscosity / (cs * cs)) + 0.5f);
+        const Scalar tau_minus = dt * ((lambda / ((tau_plus / dt) - 0.5f)) + 0.5f);
+        return TRT{tau_minus, tau_plus};
+    }
+    Scalar kinematic_shear_viscosity(const Discretization &d) const
+    {
+        const Scalar cs = d.isothermal_speed_of_sound();
+        return cs * cs * (tau_plus / d.delta_t - 0.5f);
+    }
+    Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
+    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_trt(h, tau_plus, tau_minus); }
+};
+
+struct KBC {              // src/lbm.rs:455-590
+    Scalar ks_viscosity;
+    Scalar kinematic_shear_viscosity(const Discretization &) const { return ks_viscosity; }
+    Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
+    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_kbc(h, ks_viscosity); }
+};
+
+template <typename C>
+struct Regularized {      // src/lbm.rs:596-666: only the underlying operator's viscosity is ever used
+    C underlying;
+    Scalar kinematic_shear_viscosity(const Discretization &d) const { return underlying.kinematic_shear_viscosity(d); }
+    Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
+    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_regularized(h, underlying.kinematic_shear_viscosity(Discretization())); }
 };
 
 // Value of compute_equilibrium: kept as the generating fields and evaluated on the GPU
@@ -156,16 +193,17 @@ class State {
 public:
     // State::initial(Box<L>, Geometry, Box<CollisionOperator<L>>, Discretization), :679-692.
     // `edge` is the one extension (the reference is always zero-fill).
-    static State initial(const D2Q9 &lattice, const Geometry &geometry, const BGK &collision, const Discretization &disc,
-                         int edge = CHEMSIM_LBM_EDGE_ZEROFILL, int device = -1)
+    template <typename Collision>
+    static State initial(const D2Q9 &lattice, const Geometry &geometry, const Collision &collision,
+                         const Discretization &disc, int edge = CHEMSIM_LBM_EDGE_ZEROFILL, int device = -1)
     {
         State s;
         chemsim_lbm_t *h = nullptr;
         check(chemsim_lbm_create((int)lattice.size.first, (int)lattice.size.second, CHEMSIM_LBM_F32, edge, device, &h), nullptr);
         s.h_.reset(h, [](chemsim_lbm_t *p) { chemsim_lbm_destroy(p); });
-        s.size_ = lattice.size; s.discretization = disc; s.collision = collision;
+        s.size_ = lattice.size; s.discretization = disc;
         check(chemsim_lbm_set_discretization(h, disc.delta_x, disc.delta_t), h);
-        check(chemsim_lbm_set_bgk(h, collision.tau), h);
+        check(collision.apply(h), h);                 // Box<dyn CollisionOperator<L>>, :674
         const Populations &p = lattice.populations;
         const size_t n = s.size_.first * s.size_.second;
         if (p.from_equilibrium)
@@ -211,8 +249,16 @@ public:
         return g;
     }
 
+    // render_scalar_field / render_vector_field + render_geometry (src/render.rs) on the device:
+    // RGBA8, row-major y*w+x.  mode: 0 density, 1 speed, 2 velocity, 3 momentum density (main.rs:157-174)
+    std::vector<uint8_t> render(int mode, bool overlay_geometry = true) const
+    {
+        std::vector<uint8_t> rgba(size_.first * size_.second * 4);
+        check(chemsim_lbm_render(h_.get(), mode, overlay_geometry ? 1 : 0, rgba.data(), size_.first * size_.second), h_.get());
+        return rgba;
+    }
+
     Discretization discretization;
-    BGK collision{0.0f};
     chemsim_lbm_t *handle() const { return h_.get(); }
 
 private:

@@ -3,10 +3,10 @@
 // the LBMSim frame loop handle -> step x speed_factor -> render (src/main.rs:66-177,
 // src/display.rs:121-147), headless like display::record (src/display.rs:157-185).
 //
-//   main_rs_harness W H FRAMES [paint_frame]
+//   main_rs_harness W H FRAMES [paint_frame] [bgk|regkbc]
 //
-// The collision operator is the BGK{tau: 15.0} alternative of main.rs:187 (the path
-// this repo accelerates).  Prints one line per frame for the parity test to compare
+// The collision operator is the BGK{tau: 15.0} alternative of main.rs:187 (default) or the
+// active Regularized<KBC(10)> of main.rs:198-199 ("regkbc").  Prints one line per frame for the parity test to compare
 // with the oracle: frame, state.time, total mass, density[probe], speed[probe].
 #include <cinttypes>
 #include <cstdio>
@@ -22,7 +22,7 @@ struct LBMSim {                       // src/main.rs:55-61
     State state;
 };
 
-static LBMSim initial_state(std::pair<size_t, size_t> size)   // src/main.rs:180
+static LBMSim initial_state(std::pair<size_t, size_t> size, bool regkbc)   // src/main.rs:180
 {
     const size_t w = size.first, h = size.second;
     const Discretization disc{1.0f, 1.0f};                      // :185
@@ -46,7 +46,8 @@ static LBMSim initial_state(std::pair<size_t, size_t> size)   // src/main.rs:180
         }
     LBMSim sim;
     sim.size = size;
-    sim.state = State::initial(lattice, geometry, collision, disc);                 // :314-319
+    if (regkbc) sim.state = State::initial(lattice, geometry, Regularized<KBC>{KBC{10.0f}}, disc);   // :198-199
+    else        sim.state = State::initial(lattice, geometry, collision, disc);     // :314-319
     return sim;
 }
 
@@ -69,14 +70,17 @@ int main(int argc, char **argv)
     const size_t w = std::strtoul(argv[1], nullptr, 10), h = std::strtoul(argv[2], nullptr, 10);
     const int frames = std::atoi(argv[3]);
     const int paint_frame = argc > 4 ? std::atoi(argv[4]) : -1;
+    const bool regkbc = argc > 5 && std::string(argv[5]) == "regkbc";
     try {
-        LBMSim sim = initial_state({w, h});
+        LBMSim sim = initial_state({w, h}, regkbc);
         const size_t probe = (h / 2) * w + w / 4;
         for (int f = 0; f < frames; ++f) {
             if (f == paint_frame) paint(sim, w / 4, h / 2);                         // Simulation::handle
             for (size_t s = 0; s < sim.speed_factor; ++s) sim.state.step();         // Simulation::step, :128-136
             const Matrix rho = sim.state.density();                                 // Simulation::render, :157-160
             const Matrix spd = sim.state.speed();
+            const std::vector<uint8_t> image = sim.state.render(0);                 // device-side render_scalar_field
+            if (image.size() != w * h * 4 || image[3] != 255) { std::printf("render FAILED\n"); return 1; }
             std::printf("frame %d time %.9g mass %.17g rho %.9g speed %.9g unstable %d\n", f, (double)sim.state.time(),
                         sim.state.total_mass(), (double)rho.get_underlying()[probe], (double)spd.get_underlying()[probe],
                         (int)sim.state.is_unstable());

@@ -12,18 +12,20 @@ from oracle import lbm_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def test_main_rs_shaped_cpp_driver_matches_oracle():
+@pytest.mark.parametrize("operator", ["bgk", "regkbc"])
+def test_main_rs_shaped_cpp_driver_matches_oracle(operator):
     exe = build.build_harness()
     w = h = 96
     frames, paint_frame = 12, 5
-    res = subprocess.run([exe, str(w), str(h), str(frames), str(paint_frame)], capture_output=True, text=True, timeout=120)
+    res = subprocess.run([exe, str(w), str(h), str(frames), str(paint_frame), operator], capture_output=True, text=True,
+                         timeout=120)
     assert res.returncode == 0, res.stderr
     assert "error-check ok" in res.stdout
     lines = [l for l in res.stdout.splitlines() if l.startswith("frame")]
     assert len(lines) == frames
     rho, vx, vy, solid = scenarios.main_rs(w, h, np.float32)
     f = O.compute_equilibrium(rho, vx, vy)
-    col = O.collision(O.BGK, tau=15.0)
+    col = O.collision(O.BGK, tau=15.0) if operator == "bgk" else O.collision(O.REGULARIZED)
     py, px = h // 2, w // 4
     for i, line in enumerate(lines):
         if i == paint_frame:          # main.rs:82-88: geometry becomes ONLY the 9x9 block
