@@ -151,6 +151,7 @@ def cpu_time_steps(w, h, dtype, steps, warmup):
 def cpu_baseline(w, dtype_name, budget_s=12.0):
     """Bounded sample of the workload on the host cores -> dict for the JSON line."""
     from oracle import lbm_oracle as O
+    O.use_all_cores()
     dtype = NP_DTYPE[dtype_name]
     rows = 1024                                    # a (w x 1024) band of the lattice, periodic
     t1 = cpu_time_steps(w, rows, dtype, 1, 1)
@@ -167,6 +168,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     from oracle import lbm_oracle as O
+    O.use_all_cores()
     w, hg, scaling = workload_shape(args.workload, args.gpus)
     dtype = NP_DTYPE[args.dtype]
     # size each step so that the whole run fits in ~2 minutes of CPU time

@@ -21,6 +21,15 @@ const int ORACLE_EX[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
 /* opposite directions, src/lbm.rs:298-309 */
 const int ORACLE_OPP[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
 
+void lbm_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int lbm_oracle_max_threads(void)
 {
 #ifdef _OPENMP

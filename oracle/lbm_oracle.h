@@ -77,6 +77,7 @@ ORACLE_DECL(float, f32)
 ORACLE_DECL(double, f64)
 
 int lbm_oracle_max_threads(void);
+void lbm_oracle_set_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1 */
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,13 @@ def max_threads() -> int:
     return int(lib().lbm_oracle_max_threads())
 
 
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().lbm_oracle_set_threads(n)
+    return max_threads()
+
+
 def constants(dtype, dx=1.0, dt=1.0):
     s, ct = _sfx(dtype)
     out = np.zeros(5, dtype=dtype)
