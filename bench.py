@@ -354,8 +354,9 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "strong", "weak16k"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
-                    help="multi-GPU halo: NCCL send/recv (default) or the fused peer-memory face kernel")
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"],
+                    help="multi-GPU halo: the fused peer-memory face kernel (default; falls back to NCCL if the "
+                         "neighbours cannot be mapped) or NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

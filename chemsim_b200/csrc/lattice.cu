@@ -9,6 +9,7 @@
 #include "nccl_dyn.h"
 
 #include <cmath>
+#include <ctime>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -743,10 +744,21 @@ int chemsim_lbm_destroy(chemsim_lbm_t *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
-    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P && h->comm) {
-        // neighbours may still be storing into my ghost rows: wait for everyone before unmapping
-        nccl_dyn().AllReduce(h->d_scalar, h->d_scalar + 1, 1, ncclDouble, ncclSum, h->comm, h->stream);
-        cudaStreamSynchronize(h->stream);
+    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
+        // Neighbours may still be storing into my ghost rows: wait (bounded, local polling —
+        // no collective, so a dead peer cannot hang the teardown) until both have published
+        // the last step, i.e. their last face kernel has finished.
+        const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
+        const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
+        for (int spin = 0; spin < 5000; ++spin) {
+            unsigned f[2] = {0, 0};
+            if (cudaMemcpy(f, h->p2p_flags, sizeof(f), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+            const bool up_done = !has_up || (int)(f[0] - h->step_index) >= 0;
+            const bool down_done = !has_down || (int)(f[1] - h->step_index) >= 0;
+            if (up_done && down_done) break;
+            struct timespec ts = {0, 1000000};
+            nanosleep(&ts, nullptr);
+        }
         close_p2p(h);
     }
     if (h->p2p_flags) cudaFree(h->p2p_flags);

@@ -96,3 +96,16 @@ def test_host_scalars_of_the_mirror():
     bgk = lbm.BGK(15.0)
     assert bgk.kinematic_shear_viscosity(disc) == np.float32((1.0 / 3.0) * 14.5)
     assert abs(float(bgk.kinematic_bulk_viscosity(disc)) - 2 * 14.5 / 9) < 1e-5
+
+
+def test_missing_extension_fails_loudly(tmp_path):
+    """No silent fallback: if the CUDA library is not there, importing the binding's
+    library raises instead of degrading to a CPU / PyTorch path."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['CHEMSIM_LBM_LIB'] = %r\n"
+            "from chemsim_b200 import _ffi\n"
+            "try:\n    _ffi.load()\nexcept ImportError as e:\n    print('LOUD', 'no CPU' in str(e))\n"
+            % (ROOT, str(tmp_path / "nope.so")))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "LOUD True" in res.stdout, res.stdout + res.stderr
