@@ -422,3 +422,33 @@ def test_trt_host_scalars():
     assert np.float32(trt.tau_plus) == np.float32(1.0) * (np.float32(10.0) / (np.float32(0.577350259) ** 2) + np.float32(0.5))
     assert abs(float(trt.lambda_(disc)) - 0.25) < 1e-6
     assert abs(float(trt.kinematic_shear_viscosity(disc)) - 10.0) < 1e-5
+
+
+def test_full_size_translation_equivariance_4096():
+    """Size-independent property at config-2 size: on a periodic lattice, shifting the input by
+    (dy, dx) cells shifts the output by (dy, dx) — bit for bit.  Exercises the x wrap in the
+    lane-edge loads, the y wrap and every warp/block boundary of the vector kernel."""
+    dtype = np.float32
+    w = h = 4096
+    rho, vx, vy, _ = scenarios.smooth_periodic(w, h, dtype)
+    rng = np.random.default_rng(3)
+    rho = (rho + 0.001 * rng.random((h, w))).astype(dtype)       # break the analytic symmetry
+    solid = np.zeros((h, w), np.uint8)
+    solid[1000:1040, 2000:2300] = 1
+    solid[0, 5] = 1
+    dy, dx = 37, 4093
+
+    def run(r, a, b, s):
+        st = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+        st.init_equilibrium(r, a, b)
+        st.geometry = s
+        st.step(20)
+        out = [st.population(q).array for q in (0, 2, 5, 7)]
+        st.close()
+        return out
+
+    base = run(rho, vx, vy, solid)
+    roll = lambda a: np.roll(np.roll(a, dy, axis=0), dx, axis=1)
+    shifted = run(roll(rho), roll(vx), roll(vy), roll(solid))
+    for a, b in zip(base, shifted):
+        np.testing.assert_array_equal(roll(a).view(np.uint32), b.view(np.uint32))
