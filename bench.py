@@ -154,9 +154,9 @@ def cpu_baseline(w, dtype_name, budget_s=12.0):
     O.use_all_cores()
     dtype = NP_DTYPE[dtype_name]
     rows = 1024                                    # a (w x 1024) band of the lattice, periodic
-    t1 = cpu_time_steps(w, rows, dtype, 1, 1)
-    steps = int(max(2, min(2000, budget_s / max(t1, 1e-3))))
-    dt = cpu_time_steps(w, rows, dtype, steps, 0)
+    t5 = cpu_time_steps(w, rows, dtype, 5, 3) / 5.0            # calibrate after the pages are touched
+    steps = int(max(5, min(20000, budget_s / max(t5, 1e-4))))
+    dt = cpu_time_steps(w, rows, dtype, steps, 3)
     glups = w * rows * steps / dt / 1e9
     return {"value": glups, "unit": "GLUPS", "cores": O.max_threads(), "kind": "port",
             "sample": f"{w}x{rows} band of the workload, periodic, {steps} steps, fused OpenMP restatement of lbm.rs "
