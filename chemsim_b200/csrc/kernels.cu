@@ -503,13 +503,17 @@ render_stats_final_kernel(const double *partials, int n, double cells, double *s
     const double b1 = block_sum(s1);
     __syncthreads();
     const double b2 = block_sum(s2);
-    if (threadIdx.x == 0) {
-        const double mean = b1 / cells;
-        double var = b2 / cells - mean * mean;         // population variance (af::stdev_all)
-        if (var < 0.0) var = 0.0;
-        stats[0] = mean;
-        stats[1] = sqrt(var);
-    }
+    if (threadIdx.x == 0) { stats[0] = b1; stats[1] = b2; }   // raw sums (all-reduced over the slabs when sharded)
+}
+
+// sums[0..1] = (sum, sum of squares) over `cells` cells -> stats[0..1] = (mean, population stdev)
+__global__ void render_stats_finish_kernel(const double *sums, double cells, double *stats)
+{
+    const double mean = sums[0] / cells;
+    double var = sums[1] / cells - mean * mean;        // population variance (af::stdev_all)
+    if (var < 0.0) var = 0.0;
+    stats[0] = mean;
+    stats[1] = sqrt(var);
 }
 
 // af::hsv2rgb on one pixel (h, s, v in [0,1])
@@ -730,6 +734,13 @@ int launch_render_stats(const T *src, size_t plane, int pitch, int W, int H, int
     render_stats_final_kernel<<<1, RED_THREADS, 0, s>>>(partials, blocks, (double)W * (double)H, stats);
     const int e = check_launch();
     return e ? e : 2;
+}
+
+int launch_render_stats_finish(const double *sums, double cells, double *stats, cudaStream_t s)
+{
+    render_stats_finish_kernel<<<1, 1, 0, s>>>(sums, cells, stats);
+    const int e = check_launch();
+    return e ? e : 1;
 }
 
 template <typename T>

@@ -79,10 +79,12 @@ int mass_partials_capacity();
 
 // Device-side render.rs: RGBA8 image of a macroscopic field.
 enum RenderMode : int { RENDER_DENSITY = 0, RENDER_SPEED = 1, RENDER_VELOCITY = 2, RENDER_MOMENTUM = 3 };
-// pass 1: stats[0] = mean, stats[1] = population standard deviation of the displayed scalar
-// (the field itself for DENSITY/SPEED, vx^2+vy^2 for the vector modes); partials: 2*capacity doubles
+// pass 1: sums[0] = sum, sums[1] = sum of squares of the displayed scalar over this slab (the field
+// itself for DENSITY/SPEED, vx^2+vy^2 for the vector modes); partials: 2*capacity doubles.
+// launch_render_stats_finish turns (all-reduced) sums into stats = (mean, population stdev).
 template <typename T> int launch_render_stats(const T *src, size_t plane, int pitch, int W, int H, int mode,
                                               double *partials, double *stats, cudaStream_t s);
+int launch_render_stats_finish(const double *sums, double cells, double *stats, cudaStream_t s);
 // pass 2: colour mapping (z-score -> logistic -> HSV -> RGB) + geometry overlay -> rgba[y*W+x]
 template <typename T> int launch_render_image(const T *src, size_t plane, int pitch, int W, int H, int mode,
                                               const double *stats, const uint8_t *mask, int mask_pitch,

@@ -643,7 +643,7 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
         CREATE_TRY(cudaEventCreateWithFlags(&h->ev_snap_done[i], cudaEventDisableTiming));
     }
     CREATE_TRY(cudaMalloc((void **)&h->d_partials, sizeof(double) * mass_partials_capacity()));
-    CREATE_TRY(cudaMalloc((void **)&h->d_scalar, 2 * sizeof(double)));
+    CREATE_TRY(cudaMalloc((void **)&h->d_scalar, 4 * sizeof(double)));
     CREATE_TRY(cudaMalloc((void **)&h->d_flag, sizeof(int)));
     CREATE_TRY(cudaMallocHost((void **)&h->h_scalar, 2 * sizeof(double)));
     CREATE_TRY(cudaMallocHost((void **)&h->h_flag, sizeof(int)));
@@ -1119,22 +1119,31 @@ int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t
     const int c = check_n(h, n_pixels);
     if (c) return c;
     if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
-    if (h->nranks > 1) return fail(h, CHEMSIM_LBM_ERR_UNSUPPORTED, "render needs the whole lattice on one GPU (mean/stdev are global)");
     const size_t bytes = n_pixels * 4;
     const int rs = ensure_stage(h, 1, bytes);
     if (rs) return rs;
     const uint8_t *mask = overlay_geometry ? h->mask : nullptr;
-    if (h->dtype == CHEMSIM_LBM_F32) {
+    double *sums = h->d_scalar, *stats = h->d_scalar + 2;
+    // pass 1: sum and sum of squares of the displayed scalar over this slab ...
+    if (h->dtype == CHEMSIM_LBM_F32)
         LAUNCH_TRY(h, launch_render_stats<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
-                                                 h->d_partials, h->d_scalar, h->stream));
-        LAUNCH_TRY(h, launch_render_image<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
-                                                 h->d_scalar, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
-    } else {
+                                                 h->d_partials, sums, h->stream));
+    else
         LAUNCH_TRY(h, launch_render_stats<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
-                                                  h->d_partials, h->d_scalar, h->stream));
-        LAUNCH_TRY(h, launch_render_image<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
-                                                  h->d_scalar, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
+                                                  h->d_partials, sums, h->stream));
+    // ... over the whole lattice when sharded: mean_all / stdev_all are global (collective call)
+    if (h->nranks > 1) {
+        NCCL_TRY(h, nccl_dyn().AllReduce(sums, sums, 2, ncclDouble, ncclSum, h->comm, h->stream));
+        h->launches += 1;
     }
+    LAUNCH_TRY(h, launch_render_stats_finish(sums, (double)h->W * (double)h->Hglobal, stats, h->stream));
+    // pass 2: colour mapping of this slab
+    if (h->dtype == CHEMSIM_LBM_F32)
+        LAUNCH_TRY(h, launch_render_image<float>((const float *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
+                                                 stats, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
+    else
+        LAUNCH_TRY(h, launch_render_image<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
+                                                  stats, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(rgba, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return CHEMSIM_LBM_OK;

@@ -230,7 +230,9 @@ int chemsim_lbm_total_mass_global(chemsim_lbm_t *h, double *out);
  * &state.momentum_density()) (:91-178): z-score with af::mean_all / af::stdev_all (population
  * standard deviation), logistic, HSV -> RGB, `(256*c).round().min(255).max(0) as u8`; with
  * overlay_geometry != 0 solid cells become RGB(0,0,255) as render_geometry does (:7-21).
- * rgba: n_pixels = width*height pixels of 4 bytes, row-major y*w+x, alpha 255 (display.rs:41-43). */
+ * rgba: n_pixels = width*local_height pixels of 4 bytes, row-major y*w+x, alpha 255
+ * (display.rs:41-43).  On a sharded lattice the call is collective (the mean and the standard
+ * deviation are all-reduced over the slabs) and each rank receives the image of its own rows. */
 int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t *rgba, size_t n_pixels);
 
 /* State::is_unstable (src/lbm.rs:815-818): min(f_eq,0) < 0 on this handle's cells. */

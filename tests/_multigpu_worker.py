@@ -46,8 +46,11 @@ def main():
     state.synchronize()          # also reports a halo time-out
     mine = state.populations_array()
     mass = state.total_mass(global_=True)
+    image = state.render(state.RENDER_SPEED)          # collective: mean/stdev all-reduced over the slabs
     gathered = [None] * world
     dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
+    images = [None] * world
+    dist.gather_object(image, images if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
         got = np.concatenate(gathered, axis=1)
@@ -61,6 +64,8 @@ def main():
         single.step(steps)
         single.synchronize()
         ok = ok and bool((single.populations_array().view(u) == got.view(u)).all())
+        whole = single.render(single.RENDER_SPEED).astype(np.int16)
+        ok = ok and int(np.abs(np.concatenate(images, axis=0).astype(np.int16) - whole).max()) <= 1
         ok = ok and abs(mass - O.total_mass(ref)) <= 1e-12 * abs(mass)
         ok = ok and abs(m0 - O.total_mass(f0)) <= 1e-12 * abs(m0)
         print(("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH") + f" world={world} {w}x{hg} edge={edge} {dtype_name} halo={halo}", flush=True)
