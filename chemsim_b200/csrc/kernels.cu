@@ -14,6 +14,8 @@
 // tiling (every population value is read once and written once per step).
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace chemsim {
 
 namespace {
@@ -137,6 +139,10 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     if (xv - lane >= nvec) return;                   // whole warp beyond the row
     const bool active = xv < nvec;
     const int x0 = xv * V;
+    // Programmatic dependent launch: the blocks of this step may already be resident while
+    // the previous kernel in the stream drains; nothing is read before it has completed and
+    // flushed.  A no-op when the kernel was not launched as a dependent.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // any solid cell in the 32*V cells of this warp?  (one or two 64-cell segments)
     unsigned seg_flags = 0;
     if (HAS_MASK) {
@@ -227,6 +233,9 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 {
     // MULTIROW=false: one row per block (blockDim.y == 1), so the row index and all
     // nine source-row addresses are block-uniform and live in uniform registers.
+    // let the next step's kernel start filling SM slots as soon as every block of this
+    // one has been scheduled (its blocks then wait in griddepcontrol.wait)
+    asm volatile("griddepcontrol.launch_dependents;");
     const int yi = MULTIROW ? blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
     if (yi >= a.y_count) return;                     // warp-uniform
     step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, a.y_begin + yi * a.y_stride,
@@ -594,6 +603,27 @@ const char *step_kernel_name(const StepArgs<T> &a)
     return sizeof(T) == 4 ? "step_vec_kernel<float>" : "step_vec_kernel<double>";
 }
 
+// Back-to-back step kernels are launched as programmatic dependents of each other
+// (CHEMSIM_LBM_PDL=0 in the environment restores plain stream order).
+inline bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("CHEMSIM_LBM_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename T>
+void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cudaStream_t s, const StepArgs<T> &a)
+{
+    if (!pdl_enabled()) { kernel<<<grid, block, 0, s>>>(a); return; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 template <typename T, int COL>
 void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
 {
@@ -609,8 +639,8 @@ void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
         const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
 #define CHEMSIM_LAUNCH_VEC(PX, HM)                                                                   \
         do {                                                                                         \
-            if (by == 1) step_vec_kernel<T, PX, HM, COL, false><<<grid, block, 0, s>>>(a);           \
-            else         step_vec_kernel<T, PX, HM, COL, true><<<grid, block, 0, s>>>(a);            \
+            if (by == 1) launch_chained(step_vec_kernel<T, PX, HM, COL, false>, grid, block, s, a);  \
+            else         launch_chained(step_vec_kernel<T, PX, HM, COL, true>, grid, block, s, a);   \
         } while (0)
         if (a.periodic_x) {
             if (a.has_mask) CHEMSIM_LAUNCH_VEC(true, true); else CHEMSIM_LAUNCH_VEC(true, false);
