@@ -603,27 +603,6 @@ const char *step_kernel_name(const StepArgs<T> &a)
     return sizeof(T) == 4 ? "step_vec_kernel<float>" : "step_vec_kernel<double>";
 }
 
-// Back-to-back step kernels are launched as programmatic dependents of each other
-// (CHEMSIM_LBM_PDL=0 in the environment restores plain stream order).
-inline bool pdl_enabled()
-{
-    static const bool on = [] { const char *e = getenv("CHEMSIM_LBM_PDL"); return !(e && e[0] == '0'); }();
-    return on;
-}
-
-template <typename T>
-void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cudaStream_t s, const StepArgs<T> &a)
-{
-    if (!pdl_enabled()) { kernel<<<grid, block, 0, s>>>(a); return; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, a);
-}
-
 template <typename T, int COL>
 void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
 {
@@ -657,6 +636,105 @@ void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
         const dim3 grid((rows + by - 1) / by, (a.W + bx - 1) / bx);
         step_scalar_kernel<T, COL><<<grid, block, 0, s>>>(a);
     }
+}
+
+// Back-to-back step kernels are launched as programmatic dependents of each other
+// (CHEMSIM_LBM_PDL=0 in the environment restores plain stream order).
+inline bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("CHEMSIM_LBM_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename T>
+void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cudaStream_t s, const StepArgs<T> &a)
+{
+    if (!pdl_enabled()) { kernel<<<grid, block, 0, s>>>(a); return; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+// ---- the whole slab step + halo in ONE kernel (peer-memory mode) ------------------
+// grid = (x-chunks, H); blockIdx.y = 0 -> row 0, 1 -> row H−1, r >= 2 -> row r−1, so the
+// two face rows are dispatched first: they wait for the neighbours' step flags, update
+// their rows, store the outgoing populations into the neighbours' ghost rows and publish
+// the next step early, while the remaining blocks stream through the interior.  One
+// launch per step and GPU, chained with programmatic dependent launch; no events, no
+// communication kernel, no second stream.
+template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
+__global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STEP_MIN_BLOCKS)
+step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int r = blockIdx.y;
+    const int y = r == 0 ? 0 : (r == 1 ? a.H - 1 : r - 1);
+    const int xv = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if (r >= 2) {                                    // interior row: reads no ghost row
+        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, y, xv, lane);
+        return;
+    }
+    const HaloP2P &p = a.halo;
+    if (threadIdx.x == 0) {
+        wait_flag(p.wait_up, p.step, p.error);
+        wait_flag(p.wait_down, p.step, p.error);
+    }
+    __syncthreads();
+    step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned nface = (a.H > 1 ? 2u : 1u) * gridDim.x;
+        if (atomicAdd(p.done, 1u) == nface - 1) {
+            *p.done = 0;
+            __threadfence_system();
+            if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
+            if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
+        }
+    }
+}
+
+template <typename T, int COL>
+void launch_slab_p2p_col(const StepArgs<T> &a, cudaStream_t s)
+{
+    constexpr int V = VecOf<T>::N;
+    const int nvec = a.W / V;
+    const dim3 block(STEP_THREADS, 1);
+    const dim3 grid((nvec + STEP_THREADS - 1) / STEP_THREADS, a.H);
+    if (a.periodic_x) {
+        if (a.has_mask) launch_chained(step_slab_p2p_kernel<T, true, true, COL>, grid, block, s, a);
+        else            launch_chained(step_slab_p2p_kernel<T, true, false, COL>, grid, block, s, a);
+    } else {
+        if (a.has_mask) launch_chained(step_slab_p2p_kernel<T, false, true, COL>, grid, block, s, a);
+        else            launch_chained(step_slab_p2p_kernel<T, false, false, COL>, grid, block, s, a);
+    }
+}
+
+// one block per row chunk needs full 256-thread rows; taller slabs than gridDim.y allows
+// and narrow lattices use the two-stream face/interior path instead
+template <typename T>
+bool slab_p2p_supported(const StepArgs<T> &a)
+{
+    return use_vec(a) && a.W / VecOf<T>::N >= STEP_THREADS && a.H <= 65535;
+}
+
+template <typename T>
+int launch_slab_p2p(const StepArgs<T> &a, cudaStream_t s)
+{
+    if (!slab_p2p_supported(a)) return -(int)cudaErrorInvalidValue;
+    switch (a.collision) {
+    case COL_BGK:         launch_slab_p2p_col<T, COL_BGK>(a, s); break;
+    case COL_TRT:         launch_slab_p2p_col<T, COL_TRT>(a, s); break;
+    case COL_REGULARIZED: launch_slab_p2p_col<T, COL_REGULARIZED>(a, s); break;
+    case COL_KBC:         launch_slab_p2p_col<T, COL_KBC>(a, s); break;
+    default: return -(int)cudaErrorInvalidValue;
+    }
+    const int e = check_launch();
+    return e ? e : 1;
 }
 
 template <typename T, int COL>
@@ -797,6 +875,8 @@ int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin,
     template int launch_step<T>(const StepArgs<T> &, cudaStream_t);                                                  \
     template int launch_face_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \
     template bool face_p2p_supported<T>(const StepArgs<T> &);                                                        \
+    template int launch_slab_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \
+    template bool slab_p2p_supported<T>(const StepArgs<T> &);                                                        \
     template const char *step_kernel_name<T>(const StepArgs<T> &);                                                   \
     template int launch_init_equilibrium<T>(const T *, const T *, const T *, T *, size_t, int, int, int, int,        \
                                             const Consts<T> &, cudaStream_t);                                        \

@@ -69,6 +69,9 @@ template <typename T> const char *step_kernel_name(const StepArgs<T> &a);
 // the two face rows + the halo stores into the neighbours' ghost rows, one kernel (vector widths only)
 template <typename T> int launch_face_p2p(const StepArgs<T> &a, cudaStream_t s);
 template <typename T> bool face_p2p_supported(const StepArgs<T> &a);
+// the whole slab (face rows first) + the halo stores + step flags in ONE launch per step
+template <typename T> int launch_slab_p2p(const StepArgs<T> &a, cudaStream_t s);
+template <typename T> bool slab_p2p_supported(const StepArgs<T> &a);
 // rows [row_begin, row_begin + rows) of the lattice from dense (pitch == W) fields of `rows` rows
 template <typename T> int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane,
                                                   int pitch, int W, int row_begin, int rows, const Consts<T> &k,

@@ -422,6 +422,19 @@ int step_impl(chemsim_lbm *h, int nsteps)
     }
     const int r0 = begin_sharded(h);
     if (r0) return r0;
+    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P && slab_p2p_supported(step_args<T>(h, 0, h->H))) {
+        // peer-memory mode, full-width rows: the whole step — face rows, halo stores into the
+        // neighbours' ghost rows, step flags, interior — is ONE kernel on the main stream
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_face, 0));   // the first exchange (begin_sharded)
+        for (int s = 0; s < nsteps; ++s) {
+            StepArgs<T> all = step_args<T>(h, 0, h->H);
+            fill_halo(h, all.halo);
+            LAUNCH_TRY(h, launch_slab_p2p<T>(all, h->stream));
+            h->cur ^= 1;
+            h->step_index += 1;
+        }
+        return 0;
+    }
     for (int s = 0; s < nsteps; ++s) {
         // both waits refer to the events recorded for step s−1 (or by begin_sharded)
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_face, 0));
