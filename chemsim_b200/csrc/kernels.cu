@@ -236,10 +236,14 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
     // let the next step's kernel start filling SM slots as soon as every block of this
     // one has been scheduled (its blocks then wait in griddepcontrol.wait)
     asm volatile("griddepcontrol.launch_dependents;");
-    const int yi = MULTIROW ? blockIdx.x * blockDim.y + threadIdx.y : blockIdx.x;
+    // 1-D grid, x-chunk fastest: blocks that are scheduled together work on neighbouring
+    // chunks of the same rows, so the 18 streams advance through DRAM pages in order
+    // (measured +4 % over row-fastest block order).
+    const int rg = blockIdx.x / a.xchunks, xc = blockIdx.x - rg * a.xchunks;
+    const int yi = MULTIROW ? rg * blockDim.y + threadIdx.y : rg;
     if (yi >= a.y_count) return;                     // warp-uniform
     step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, a.y_begin + yi * a.y_stride,
-                                                       blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31);
+                                                       xc * blockDim.x + threadIdx.x, threadIdx.x & 31);
 }
 
 // ---- fused face update + halo exchange over peer memory ------------------------
@@ -603,41 +607,6 @@ const char *step_kernel_name(const StepArgs<T> &a)
     return sizeof(T) == 4 ? "step_vec_kernel<float>" : "step_vec_kernel<double>";
 }
 
-template <typename T, int COL>
-void launch_step_col(const StepArgs<T> &a, cudaStream_t s)
-{
-    const int rows = a.y_count;
-    if (use_vec(a)) {
-        constexpr int V = VecOf<T>::N;
-        const int nvec = a.W / V;
-        int bx = ((nvec + 31) / 32) * 32;
-        if (bx > STEP_THREADS) bx = STEP_THREADS;
-        int by = STEP_THREADS / bx;
-        if (by > rows) by = rows;
-        const dim3 block(bx, by);
-        const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
-#define CHEMSIM_LAUNCH_VEC(PX, HM)                                                                   \
-        do {                                                                                         \
-            if (by == 1) launch_chained(step_vec_kernel<T, PX, HM, COL, false>, grid, block, s, a);  \
-            else         launch_chained(step_vec_kernel<T, PX, HM, COL, true>, grid, block, s, a);   \
-        } while (0)
-        if (a.periodic_x) {
-            if (a.has_mask) CHEMSIM_LAUNCH_VEC(true, true); else CHEMSIM_LAUNCH_VEC(true, false);
-        } else {
-            if (a.has_mask) CHEMSIM_LAUNCH_VEC(false, true); else CHEMSIM_LAUNCH_VEC(false, false);
-        }
-#undef CHEMSIM_LAUNCH_VEC
-    } else {
-        int bx = ((a.W + 31) / 32) * 32;
-        if (bx > STEP_THREADS) bx = STEP_THREADS;
-        int by = STEP_THREADS / bx;
-        if (by > rows) by = rows;
-        const dim3 block(bx, by);
-        const dim3 grid((rows + by - 1) / by, (a.W + bx - 1) / bx);
-        step_scalar_kernel<T, COL><<<grid, block, 0, s>>>(a);
-    }
-}
-
 // Back-to-back step kernels are launched as programmatic dependents of each other
 // (CHEMSIM_LBM_PDL=0 in the environment restores plain stream order).
 inline bool pdl_enabled()
@@ -659,9 +628,46 @@ void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cu
     cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
+template <typename T, int COL>
+void launch_step_col(const StepArgs<T> &a_in, cudaStream_t s)
+{
+    const int rows = a_in.y_count;
+    if (use_vec(a_in)) {
+        constexpr int V = VecOf<T>::N;
+        const int nvec = a_in.W / V;
+        int bx = ((nvec + 31) / 32) * 32;
+        if (bx > STEP_THREADS) bx = STEP_THREADS;
+        int by = STEP_THREADS / bx;
+        if (by > rows) by = rows;
+        const dim3 block(bx, by);
+        StepArgs<T> a = a_in;
+        a.xchunks = (nvec + bx - 1) / bx;
+        const dim3 grid((unsigned)a.xchunks * (unsigned)((rows + by - 1) / by));
+#define CHEMSIM_LAUNCH_VEC(PX, HM)                                                                   \
+        do {                                                                                         \
+            if (by == 1) launch_chained(step_vec_kernel<T, PX, HM, COL, false>, grid, block, s, a);  \
+            else         launch_chained(step_vec_kernel<T, PX, HM, COL, true>, grid, block, s, a);   \
+        } while (0)
+        if (a.periodic_x) {
+            if (a.has_mask) CHEMSIM_LAUNCH_VEC(true, true); else CHEMSIM_LAUNCH_VEC(true, false);
+        } else {
+            if (a.has_mask) CHEMSIM_LAUNCH_VEC(false, true); else CHEMSIM_LAUNCH_VEC(false, false);
+        }
+#undef CHEMSIM_LAUNCH_VEC
+    } else {
+        int bx = ((a_in.W + 31) / 32) * 32;
+        if (bx > STEP_THREADS) bx = STEP_THREADS;
+        int by = STEP_THREADS / bx;
+        if (by > rows) by = rows;
+        const dim3 block(bx, by);
+        const dim3 grid((rows + by - 1) / by, (a_in.W + bx - 1) / bx);
+        step_scalar_kernel<T, COL><<<grid, block, 0, s>>>(a_in);
+    }
+}
+
 // ---- the whole slab step + halo in ONE kernel (peer-memory mode) ------------------
-// grid = (x-chunks, H); blockIdx.y = 0 -> row 0, 1 -> row H−1, r >= 2 -> row r−1, so the
-// two face rows are dispatched first: they wait for the neighbours' step flags, update
+// 1-D grid of x-chunks x H blocks, x-chunk fastest; row slot r = 0 -> row 0, 1 -> row H−1,
+// r >= 2 -> row r−1, so the two face rows are dispatched first: they wait for the neighbours' step flags, update
 // their rows, store the outgoing populations into the neighbours' ghost rows and publish
 // the next step early, while the remaining blocks stream through the interior.  One
 // launch per step and GPU, chained with programmatic dependent launch; no events, no
@@ -671,9 +677,9 @@ __global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STE
 step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
 {
     asm volatile("griddepcontrol.launch_dependents;");
-    const int r = blockIdx.y;
+    const int r = blockIdx.x / a.xchunks, xc = blockIdx.x - r * a.xchunks;
     const int y = r == 0 ? 0 : (r == 1 ? a.H - 1 : r - 1);
-    const int xv = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int xv = xc * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if (r >= 2) {                                    // interior row: reads no ghost row
         step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, y, xv, lane);
         return;
@@ -688,7 +694,7 @@ step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned nface = (a.H > 1 ? 2u : 1u) * gridDim.x;
+        const unsigned nface = (a.H > 1 ? 2u : 1u) * (unsigned)a.xchunks;
         if (atomicAdd(p.done, 1u) == nface - 1) {
             *p.done = 0;
             __threadfence_system();
@@ -699,12 +705,14 @@ step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
 }
 
 template <typename T, int COL>
-void launch_slab_p2p_col(const StepArgs<T> &a, cudaStream_t s)
+void launch_slab_p2p_col(const StepArgs<T> &a_in, cudaStream_t s)
 {
     constexpr int V = VecOf<T>::N;
-    const int nvec = a.W / V;
+    const int nvec = a_in.W / V;
     const dim3 block(STEP_THREADS, 1);
-    const dim3 grid((nvec + STEP_THREADS - 1) / STEP_THREADS, a.H);
+    StepArgs<T> a = a_in;
+    a.xchunks = (nvec + STEP_THREADS - 1) / STEP_THREADS;
+    const dim3 grid((unsigned)a.xchunks * (unsigned)a.H);
     if (a.periodic_x) {
         if (a.has_mask) launch_chained(step_slab_p2p_kernel<T, true, true, COL>, grid, block, s, a);
         else            launch_chained(step_slab_p2p_kernel<T, true, false, COL>, grid, block, s, a);
@@ -714,12 +722,12 @@ void launch_slab_p2p_col(const StepArgs<T> &a, cudaStream_t s)
     }
 }
 
-// one block per row chunk needs full 256-thread rows; taller slabs than gridDim.y allows
-// and narrow lattices use the two-stream face/interior path instead
+// one block per row chunk needs full 256-thread rows; narrower lattices use the
+// two-stream face/interior path instead
 template <typename T>
 bool slab_p2p_supported(const StepArgs<T> &a)
 {
-    return use_vec(a) && a.W / VecOf<T>::N >= STEP_THREADS && a.H <= 65535;
+    return use_vec(a) && a.W / VecOf<T>::N >= STEP_THREADS;
 }
 
 template <typename T>

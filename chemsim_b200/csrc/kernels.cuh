@@ -32,6 +32,7 @@ struct StepArgs {
     int W, H;              // local lattice: W columns, H rows
     int y_begin, y_count;  // this launch updates rows y_begin + i*y_stride, i in [0, y_count)
     int y_stride;          // 1 for a band of rows; H−1 for the two face rows {0, H−1} of a slab
+    int xchunks;           // blocks per row (set by the launcher): block b works on chunk b % xchunks of row group b / xchunks
     int wrap_y;            // 1: rows −1/H alias rows H−1/0 (periodic, unsharded); 0: read the ghost rows
     int periodic_x;        // 1: wrap in x; 0: zero-fill (reference)
     const uint8_t *mask;   // H rows of mask_pitch bytes, non-zero = solid

@@ -197,6 +197,7 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.y_begin = y_begin;
     a.y_count = y_count;
     a.y_stride = y_stride;
+    a.xchunks = 1;
     a.wrap_y = (h->edge == CHEMSIM_LBM_EDGE_PERIODIC && h->nranks == 1) ? 1 : 0;
     a.periodic_x = h->edge == CHEMSIM_LBM_EDGE_PERIODIC ? 1 : 0;
     a.mask = h->mask;
