@@ -35,12 +35,13 @@ template <> struct VecOf<double> { using type = double2; static constexpr int N 
 // .nc is legal.  NC=false (coherent) is used by the P2P face kernel, whose ghost
 // rows are written by the neighbouring GPU while the kernel may already be resident.
 // Predication instead of `if` keeps every load of a thread in ONE straight-line
-// batch: all of them are in flight before the first use.
+// batch: all of them are in flight before the first use.  The "memory" clobber keeps
+// the compiler from hoisting a load above griddepcontrol.wait or the halo flag wait.
 #define CHEMSIM_LDG_BODY(NCSTR)                                                                       \
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"                                             \
         "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"                    \
         "@q ld.global" NCSTR ".v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"                                   \
-        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred))
+        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred) : "memory")
 template <bool NC>
 __device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4])
 {
@@ -51,7 +52,7 @@ __device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4]
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"                                             \
         "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"                                                        \
         "@q ld.global" NCSTR ".v2.f64 {%0, %1}, [%2];\n\t}"                                           \
-        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred))
+        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred) : "memory")
 template <bool NC>
 __device__ __forceinline__ void ldg_vec(const double *p, bool pred, double (&v)[2])
 {
@@ -63,9 +64,9 @@ __device__ __forceinline__ float ldg_one(const float *p, bool pred)
 {
     float v;
     if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
-                : "=&f"(v) : "l"(p), "r"((int)pred));
+                : "=&f"(v) : "l"(p), "r"((int)pred) : "memory");
     else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.f32 %0, [%1];\n\t}"
-                : "=&f"(v) : "l"(p), "r"((int)pred));
+                : "=&f"(v) : "l"(p), "r"((int)pred) : "memory");
     return v;
 }
 template <bool NC>
@@ -73,9 +74,9 @@ __device__ __forceinline__ double ldg_one(const double *p, bool pred)
 {
     double v;
     if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
-                : "=&d"(v) : "l"(p), "r"((int)pred));
+                : "=&d"(v) : "l"(p), "r"((int)pred) : "memory");
     else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.f64 %0, [%1];\n\t}"
-                : "=&d"(v) : "l"(p), "r"((int)pred));
+                : "=&d"(v) : "l"(p), "r"((int)pred) : "memory");
     return v;
 }
 __device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
@@ -99,14 +100,14 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
 {
     unsigned v;
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
-        : "=&r"(v) : "l"(p), "r"((int)pred));
+        : "=&r"(v) : "l"(p), "r"((int)pred) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const double *)
 {
     unsigned short v;
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b16 %0, 0;\n\t@q ld.global.nc.u16 %0, [%1];\n\t}"
-        : "=&h"(v) : "l"(p), "r"((int)pred));
+        : "=&h"(v) : "l"(p), "r"((int)pred) : "memory");
     return v;
 }
 
@@ -118,6 +119,13 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
 #define CHEMSIM_STEP_MIN_BLOCKS 4   // <= 64 registers: 4 x 256 threads per SM (ptxas otherwise takes 88 for f64)
 #endif
 constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
+// resident blocks per SM the step kernels are compiled for: BGK fits 64 registers in both
+// precisions; the f64 TRT / Regularized bodies need ~80 (3 blocks), KBC is left unconstrained
+template <typename T, int COL>
+constexpr int step_min_blocks()
+{
+    return COL == COL_KBC ? 1 : (COL != COL_BGK && sizeof(T) == 8 ? 3 : CHEMSIM_STEP_MIN_BLOCKS);
+}
 
 // ---- the fused step, vector form ---------------------------------------------
 // Thread (tx, ty) of block (bx, by) updates the V = 16/sizeof(T) cells
@@ -228,7 +236,7 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
 }
 
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
-__global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<T, COL>())
 step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 {
     // MULTIROW=false: one row per block (blockDim.y == 1), so the row index and all
@@ -673,7 +681,7 @@ void launch_step_col(const StepArgs<T> &a_in, cudaStream_t s)
 // launch per step and GPU, chained with programmatic dependent launch; no events, no
 // communication kernel, no second stream.
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
-__global__ void __launch_bounds__(STEP_THREADS, COL == COL_KBC ? 1 : CHEMSIM_STEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<T, COL>())
 step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
 {
     asm volatile("griddepcontrol.launch_dependents;");
