@@ -35,13 +35,15 @@ template <> struct VecOf<double> { using type = double2; static constexpr int N 
 // .nc is legal.  NC=false (coherent) is used by the P2P face kernel, whose ghost
 // rows are written by the neighbouring GPU while the kernel may already be resident.
 // Predication instead of `if` keeps every load of a thread in ONE straight-line
-// batch: all of them are in flight before the first use.  The "memory" clobber keeps
-// the compiler from hoisting a load above griddepcontrol.wait or the halo flag wait.
+// batch: all of them are in flight before the first use.  The asm statements carry no
+// memory dependence of their own: what keeps them behind griddepcontrol.wait and the halo
+// flag wait is a data dependence — every address is derived from an "order token" (always
+// 0, but opaque to the compiler) that those waits produce (see order_after_*).
 #define CHEMSIM_LDG_BODY(NCSTR)                                                                       \
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"                                             \
         "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"                    \
         "@q ld.global" NCSTR ".v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"                                   \
-        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred) : "memory")
+        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred))
 template <bool NC>
 __device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4])
 {
@@ -52,7 +54,7 @@ __device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4]
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"                                             \
         "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"                                                        \
         "@q ld.global" NCSTR ".v2.f64 {%0, %1}, [%2];\n\t}"                                           \
-        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred) : "memory")
+        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred))
 template <bool NC>
 __device__ __forceinline__ void ldg_vec(const double *p, bool pred, double (&v)[2])
 {
@@ -64,9 +66,9 @@ __device__ __forceinline__ float ldg_one(const float *p, bool pred)
 {
     float v;
     if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
-                : "=&f"(v) : "l"(p), "r"((int)pred) : "memory");
+                : "=&f"(v) : "l"(p), "r"((int)pred));
     else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.f32 %0, [%1];\n\t}"
-                : "=&f"(v) : "l"(p), "r"((int)pred) : "memory");
+                : "=&f"(v) : "l"(p), "r"((int)pred));
     return v;
 }
 template <bool NC>
@@ -74,9 +76,9 @@ __device__ __forceinline__ double ldg_one(const double *p, bool pred)
 {
     double v;
     if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
-                : "=&d"(v) : "l"(p), "r"((int)pred) : "memory");
+                : "=&d"(v) : "l"(p), "r"((int)pred));
     else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.f64 %0, [%1];\n\t}"
-                : "=&d"(v) : "l"(p), "r"((int)pred) : "memory");
+                : "=&d"(v) : "l"(p), "r"((int)pred));
     return v;
 }
 __device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
@@ -100,14 +102,14 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
 {
     unsigned v;
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
-        : "=&r"(v) : "l"(p), "r"((int)pred) : "memory");
+        : "=&r"(v) : "l"(p), "r"((int)pred));
     return v;
 }
 __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const double *)
 {
     unsigned short v;
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b16 %0, 0;\n\t@q ld.global.nc.u16 %0, [%1];\n\t}"
-        : "=&h"(v) : "l"(p), "r"((int)pred) : "memory");
+        : "=&h"(v) : "l"(p), "r"((int)pred));
     return v;
 }
 
@@ -138,8 +140,18 @@ constexpr int step_min_blocks()
 // The update of V cells of row y by one thread (see the kernel comment above).
 // P2P=true additionally stores the populations that leave the slab through this face
 // row straight into the neighbouring GPU's ghost row (peer-mapped memory, NVLink).
+// griddepcontrol.wait as an opaque producer of 0: adding the result to a base pointer
+// orders every load derived from it after the wait.
+__device__ __forceinline__ int order_after_grid_dependency()
+{
+    int tok;
+    asm volatile("griddepcontrol.wait;\n\tmov.u32 %0, 0;" : "=r"(tok) : : "memory");
+    return tok;
+}
+
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool P2P>
-__device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y, const int xv, const int lane)
+__device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y, const int xv, const int lane,
+                                              const int halo_tok)
 {
     constexpr int V = VecOf<T>::N;
     constexpr bool NC = !P2P;
@@ -149,12 +161,14 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     const int x0 = xv * V;
     // Programmatic dependent launch: the blocks of this step may already be resident while
     // the previous kernel in the stream drains; nothing is read before it has completed and
-    // flushed.  A no-op when the kernel was not launched as a dependent.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // flushed (a no-op when the kernel was not launched as a dependent).  `tok` is 0.
+    const int tok = order_after_grid_dependency() + halo_tok;
+    const T *src = a.src + tok;
+    const uint8_t *mask = a.mask + tok, *mask_flags = a.mask_flags + tok;
     // any solid cell in the 32*V cells of this warp?  (one or two 64-cell segments)
     unsigned seg_flags = 0;
     if (HAS_MASK) {
-        const uint8_t *fl = a.mask_flags + (size_t)y * a.flag_pitch + ((xv - lane) * V) / MASK_SEGMENT;
+        const uint8_t *fl = mask_flags + (size_t)y * a.flag_pitch + ((xv - lane) * V) / MASK_SEGMENT;
         seg_flags = (V == 4) ? *reinterpret_cast<const unsigned short *>(fl) : *fl;
     }
     // which lanes must fetch the element their neighbour lane cannot supply
@@ -171,7 +185,7 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     for (int q = 0; q < Q; ++q) {
         int sy = y - ey_of(q);
         if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
-        const T *row = a.src + (size_t)q * a.plane + (size_t)(sy + 1) * a.pitch;
+        const T *row = src + (size_t)q * a.plane + (size_t)(sy + 1) * a.pitch;
         ldg_vec<NC>(row + x0, active, v[q]);
         if (ex_of(q) == 1)       e[q] = ldg_one<NC>(row + left_x, need_left);
         else if (ex_of(q) == -1) e[q] = ldg_one<NC>(row + right_x, need_right);
@@ -179,7 +193,7 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     }
     unsigned maskw = 0;
     if (HAS_MASK && seg_flags != 0)                  // warp-uniform
-        maskw = ldg_mask(a.mask + (size_t)y * a.mask_pitch + x0, active, (const T *)nullptr);
+        maskw = ldg_mask(mask + (size_t)y * a.mask_pitch + x0, active, (const T *)nullptr);
 
     // ---- phase 2: shift the x-streaming populations by one element -------------
     T g[Q][V];
@@ -251,7 +265,7 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
     const int yi = MULTIROW ? rg * blockDim.y + threadIdx.y : rg;
     if (yi >= a.y_count) return;                     // warp-uniform
     step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, a.y_begin + yi * a.y_stride,
-                                                       xc * blockDim.x + threadIdx.x, threadIdx.x & 31);
+                                                       xc * blockDim.x + threadIdx.x, threadIdx.x & 31, 0);
 }
 
 // ---- fused face update + halo exchange over peer memory ------------------------
@@ -276,20 +290,31 @@ __device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned want, i
     __threadfence_system();
 }
 
+// One thread waits for both neighbours' step flags, the block follows through a barrier.
+// Returns 0 through shared memory: an order token for the ghost-row loads (see ldg_*).
+__device__ __forceinline__ int order_after_halo_flags(const HaloP2P &p)
+{
+    __shared__ int token;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        wait_flag(p.wait_up, p.step, p.error);
+        wait_flag(p.wait_down, p.step, p.error);
+        token = 0;
+    }
+    __syncthreads();
+    return *reinterpret_cast<volatile int *>(&token);
+}
+
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
 __global__ void __launch_bounds__(STEP_THREADS, 1)
 step_face_p2p_kernel(const __grid_constant__ StepArgs<T> a)
 {
     const HaloP2P &p = a.halo;
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        wait_flag(p.wait_up, p.step, p.error);
-        wait_flag(p.wait_down, p.step, p.error);
-    }
-    __syncthreads();
+    const int halo_tok = order_after_halo_flags(p);
     const int yi = blockIdx.x * blockDim.y + threadIdx.y;
     if (yi < a.y_count)
         step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, a.y_begin + yi * a.y_stride,
-                                                          blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31);
+                                                          blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31,
+                                                          halo_tok);
     __threadfence_system();                          // my stores (local and peer) are visible system-wide ...
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -689,16 +714,12 @@ step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     const int y = r == 0 ? 0 : (r == 1 ? a.H - 1 : r - 1);
     const int xv = xc * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if (r >= 2) {                                    // interior row: reads no ghost row
-        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, y, xv, lane);
+        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, y, xv, lane, 0);
         return;
     }
     const HaloP2P &p = a.halo;
-    if (threadIdx.x == 0) {
-        wait_flag(p.wait_up, p.step, p.error);
-        wait_flag(p.wait_down, p.step, p.error);
-    }
-    __syncthreads();
-    step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane);
+    const int halo_tok = order_after_halo_flags(p);
+    step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane, halo_tok);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
