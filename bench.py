@@ -12,7 +12,9 @@ lattice.  Workloads:
   config3  8192x2048 channel with walls + cylinder mask (per GPU)
   strong   32768x32768 global lattice, y-slab sharded over the N GPUs (config 4)
   weak16k  16384x16384 per GPU (config 5)
-One JSON line is printed by rank 0.
+Multi-GPU runs shard the lattice into y-slabs, one process per GPU; `--halo p2p` (default) uses the
+fused peer-memory halo (falls back to NCCL when the neighbours cannot be mapped), `--halo nccl` the
+NCCL send/recv exchange.  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -148,7 +150,7 @@ def cpu_time_steps(w, h, dtype, steps, warmup):
     return dt
 
 
-def cpu_baseline(w, dtype_name, budget_s=12.0):
+def cpu_baseline(w, dtype_name, budget_s=25.0):
     """Bounded sample of the workload on the host cores -> dict for the JSON line."""
     from oracle import lbm_oracle as O
     O.use_all_cores()

@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
     return v;
 }
 
-// Build-time tunables (defaults are the measured best; tools/variants.sh sweeps them).
+// Build-time tunables (defaults are the measured best; tools/variants.py sweeps them).
 #ifndef CHEMSIM_STEP_THREADS
 #define CHEMSIM_STEP_THREADS 256
 #endif
