@@ -241,7 +241,12 @@ def run_gpu_arm(args):
 
     dtype = NP_DTYPE[args.dtype]
     w, hg, scaling = workload_shape(args.workload, world)
-    state = lbm.State.create((w, hg), lbm.BGK(TAU), lbm.Discretization(1.0, 1.0), dtype=dtype,
+    disc = lbm.Discretization(1.0, 1.0)
+    collision = {"bgk": lambda: lbm.BGK(TAU),                                   # nu = (tau - 1/2)/3 = 0.1
+                 "trt": lambda: lbm.TRT.new(0.25, 0.1, disc, dtype),           # same viscosity, magic lambda 1/4
+                 "regularized": lambda: lbm.Regularized.new(lbm.KBC.new(0.1)),  # main.rs:198-199's operator
+                 "kbc": lambda: lbm.KBC.new(0.1)}[args.collision]()
+    state = lbm.State.create((w, hg), collision, disc, dtype=dtype,
                              edge=lbm.EDGE_PERIODIC, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
     if args.halo == "p2p" and world > 1:
         state.enable_p2p_halo()
@@ -319,7 +324,8 @@ def run_gpu_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": args.workload, "lattice": f"{w}x{hg}", "per_gpu": f"{w}x{hl}",
-                       "collision": "BGK tau=0.8", "edge": "periodic", "sharding": f"y-slabs x{world}",
+                       "collision": "BGK tau=0.8" if args.collision == "bgk" else f"{args.collision} nu=0.1",
+                       "edge": "periodic", "sharding": f"y-slabs x{world}",
                        "halo": state.halo_mode() if world > 1 else "none",
                        "l2": "working set %.2f GiB per GPU >> 126 MB L2 (no flush needed)" % (2 * 9 * w * hl * (bpc / 18) / 2**30),
                        "kernel": state.step_kernel_name(),
@@ -356,6 +362,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "strong", "weak16k"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--collision", default="bgk", choices=["bgk", "trt", "regularized", "kbc"],
+                    help="collision operator of the step (default: BGK, BASELINE.json's metric)")
     ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"],
                     help="multi-GPU halo: the fused peer-memory face kernel (default; falls back to NCCL if the "
                          "neighbours cannot be mapped) or NCCL send/recv")
