@@ -452,3 +452,28 @@ def test_full_size_translation_equivariance_4096():
     shifted = run(roll(rho), roll(vx), roll(vy), roll(solid))
     for a, b in zip(base, shifted):
         np.testing.assert_array_equal(roll(a).view(np.uint32), b.view(np.uint32))
+
+
+def test_large_lattice_16384_needs_64bit_offsets():
+    """Maximum-size style case: 16384^2 f32 (18 GiB of populations, plane offsets beyond 2^31
+    elements), initialised in row chunks; a uniform periodic state must stay a fixed point and
+    the f64 mass reduction must equal the analytic value."""
+    dtype = np.float32
+    w = h = 16384
+    state = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+    chunk = 2048
+    rho = np.ones((chunk, w), dtype)
+    vx = np.full((chunk, w), 0.03, dtype)
+    vy = np.full((chunk, w), -0.02, dtype)
+    for r in range(0, h, chunk):
+        state.init_equilibrium_rows(r, rho, vx, vy)
+    f_cell = O.compute_equilibrium(rho[:1, :1], vx[:1, :1], vy[:1, :1])[:, 0, 0]      # the nine values of one cell
+    mass0 = state.total_mass()
+    assert abs(mass0 - float(np.sum(f_cell.astype(np.float64))) * w * h) <= 1e-9 * mass0
+    state.step(10)
+    for q in (0, 8):                                   # first and last plane (largest offsets)
+        got = state.population(q).array
+        np.testing.assert_allclose(got[::1021, ::509], f_cell[q], rtol=2e-6)
+        assert got[h - 1, w - 1] == got[0, 0]
+    assert abs(state.total_mass() - mass0) <= 2e-7 * mass0      # ~10 steps of the (sum w - 1)/tau drift
+    state.close()
