@@ -10,6 +10,7 @@
 
 #include <cmath>
 #include <ctime>
+#include <unistd.h>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -118,6 +119,7 @@ struct chemsim_lbm {
     unsigned *peer_up_flags = nullptr, *peer_down_flags = nullptr;
     int peer_up_H = 0, peer_down_H = 0;
     bool peer_same = false;                         // both neighbours are the same rank (nranks == 2)
+    bool peer_up_ipc = false, peer_down_ipc = false;   // mapped through cudaIpc (other process) or raw (same process)
     bool have_populations = false;
 
     float time_f = 0.f;
@@ -282,20 +284,51 @@ struct P2PInfo {                 // what the ranks tell each other (all-gathered
     cudaIpcMemHandle_t flags;
     int H;
     int ok;
-    char pad[256 - 3 * sizeof(cudaIpcMemHandle_t) - 2 * sizeof(int)];
+    // ranks that live in the SAME process (one host thread per GPU) cannot open each other's
+    // IPC handles; they use the raw device pointers (unified addressing) + peer access
+    long long pid;
+    int device;
+    int pad0;
+    void *raw_buf[2];
+    void *raw_flags;
+    char pad[512 - 3 * sizeof(cudaIpcMemHandle_t) - 4 * sizeof(int) - sizeof(long long) - 3 * sizeof(void *)];
 };
-static_assert(sizeof(P2PInfo) == 256, "P2PInfo layout");
+static_assert(sizeof(P2PInfo) == 512, "P2PInfo layout");
+
+// Map one neighbour's population buffers and flag block.  Returns false on failure.
+bool map_peer(chemsim_lbm *h, const P2PInfo &peer, void *(&buf)[2], unsigned *&flags, bool &via_ipc)
+{
+    if (peer.pid == (long long)getpid()) {          // same process: direct peer pointers
+        via_ipc = false;
+        if (peer.device != h->device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, h->device, peer.device) != cudaSuccess || !can) return false;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(peer.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+            cudaGetLastError();
+        }
+        buf[0] = peer.raw_buf[0]; buf[1] = peer.raw_buf[1];
+        flags = (unsigned *)peer.raw_flags;
+        return true;
+    }
+    via_ipc = true;
+    const unsigned fl = cudaIpcMemLazyEnablePeerAccess;
+    for (int b = 0; b < 2; ++b)
+        if (cudaIpcOpenMemHandle(&buf[b], peer.buf[b], fl) != cudaSuccess) return false;
+    return cudaIpcOpenMemHandle((void **)&flags, peer.flags, fl) == cudaSuccess;
+}
 
 void close_p2p(chemsim_lbm *h)
 {
     for (int b = 0; b < 2; ++b) {
-        if (h->peer_up_buf[b]) cudaIpcCloseMemHandle(h->peer_up_buf[b]);
-        if (h->peer_down_buf[b] && !h->peer_same) cudaIpcCloseMemHandle(h->peer_down_buf[b]);
+        if (h->peer_up_buf[b] && h->peer_up_ipc) cudaIpcCloseMemHandle(h->peer_up_buf[b]);
+        if (h->peer_down_buf[b] && h->peer_down_ipc && !h->peer_same) cudaIpcCloseMemHandle(h->peer_down_buf[b]);
         h->peer_up_buf[b] = h->peer_down_buf[b] = nullptr;
     }
-    if (h->peer_up_flags) cudaIpcCloseMemHandle(h->peer_up_flags);
-    if (h->peer_down_flags && !h->peer_same) cudaIpcCloseMemHandle(h->peer_down_flags);
+    if (h->peer_up_flags && h->peer_up_ipc) cudaIpcCloseMemHandle(h->peer_up_flags);
+    if (h->peer_down_flags && h->peer_down_ipc && !h->peer_same) cudaIpcCloseMemHandle(h->peer_down_flags);
     h->peer_up_flags = h->peer_down_flags = nullptr;
+    cudaGetLastError();
 }
 
 // Collective over all ranks of the lattice.  Every rank ends in the same mode.
@@ -312,6 +345,8 @@ int enable_p2p(chemsim_lbm *h)
     std::memset(&mine, 0, sizeof(mine));
     mine.H = h->H;
     mine.ok = 1;
+    mine.pid = (long long)getpid();
+    mine.device = h->device;
     if (!h->p2p_flags) {
         if (cudaMalloc((void **)&h->p2p_flags, 4 * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
         else if (cudaMemset(h->p2p_flags, 0, 4 * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
@@ -325,6 +360,7 @@ int enable_p2p(chemsim_lbm *h)
         mine.ok = 0;
         cudaGetLastError();
     }
+    mine.raw_buf[0] = h->buf[0]; mine.raw_buf[1] = h->buf[1]; mine.raw_flags = h->p2p_flags;
     // all-gather the handles
     char *d_all = nullptr;
     CUDA_TRY(h, cudaMalloc((void **)&d_all, sizeof(P2PInfo) * (h->nranks + 1)));
@@ -338,22 +374,18 @@ int enable_p2p(chemsim_lbm *h)
     for (int r = 0; r < h->nranks; ++r) ok &= info[r].ok;
     // map the neighbours' buffers
     if (ok) {
-        const unsigned fl = cudaIpcMemLazyEnablePeerAccess;
         if (has_up) {
             h->peer_up_H = info[up].H;
-            for (int b = 0; b < 2 && ok; ++b)
-                if (cudaIpcOpenMemHandle(&h->peer_up_buf[b], info[up].buf[b], fl) != cudaSuccess) ok = 0;
-            if (ok && cudaIpcOpenMemHandle((void **)&h->peer_up_flags, info[up].flags, fl) != cudaSuccess) ok = 0;
+            if (!map_peer(h, info[up], h->peer_up_buf, h->peer_up_flags, h->peer_up_ipc)) ok = 0;
         }
         if (has_down && ok) {
             h->peer_down_H = info[down].H;
             if (h->peer_same) {
                 h->peer_down_buf[0] = h->peer_up_buf[0]; h->peer_down_buf[1] = h->peer_up_buf[1];
                 h->peer_down_flags = h->peer_up_flags;
-            } else {
-                for (int b = 0; b < 2 && ok; ++b)
-                    if (cudaIpcOpenMemHandle(&h->peer_down_buf[b], info[down].buf[b], fl) != cudaSuccess) ok = 0;
-                if (ok && cudaIpcOpenMemHandle((void **)&h->peer_down_flags, info[down].flags, fl) != cudaSuccess) ok = 0;
+                h->peer_down_ipc = h->peer_up_ipc;
+            } else if (!map_peer(h, info[down], h->peer_down_buf, h->peer_down_flags, h->peer_down_ipc)) {
+                ok = 0;
             }
         }
         if (!ok) cudaGetLastError();

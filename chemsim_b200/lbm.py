@@ -481,3 +481,110 @@ def halo_plan(rank: int, nranks: int, edge: int):
     n = C.c_int()
     _ffi.check(_ffi.load().chemsim_lbm_halo_plan(rank, nranks, edge, buf, C.byref(n)), None)
     return [(bool(m.is_send), m.peer, m.q, m.row) for m in buf[: n.value]]
+
+
+class MultiState:
+    """One lattice sharded over several GPUs of the box, driven from ONE process — what an
+    unchanged single-process caller (the reference's main.rs) needs in order to use more than
+    one GPU.  It owns one y-slab `State` per device; collective calls (creation, the switch to
+    the peer-memory halo, the first exchange inside step, sharded render / global mass) are
+    issued from one host thread per slab (ctypes releases the GIL), everything else is a loop.
+    Slabs of the same process map each other's memory directly (peer access), not through
+    cudaIpc.  Same readout surface as `State`, fields concatenated over the slabs."""
+
+    def __init__(self, size, collision, discretization=Discretization(), dtype=Scalar, edge=EDGE_ZEROFILL,
+                 devices=(0,), p2p=True):
+        from concurrent.futures import ThreadPoolExecutor
+        self.devices = list(devices)
+        n = len(self.devices)
+        self._pool = ThreadPoolExecutor(max_workers=n)
+        self.dtype = np.dtype(dtype)
+        self.width, self.global_height = size
+        nccl_id = nccl_unique_id() if n > 1 else None
+        self.slabs = list(self._pool.map(
+            lambda r: State.create(size, collision, discretization, dtype, edge, self.devices[r], r, n, nccl_id),
+            range(n)))
+        if p2p and n > 1:
+            self._each(lambda s: s.enable_p2p_halo())
+        self.collision, self.discretization = collision, discretization
+
+    def _each(self, fn):
+        return list(self._pool.map(fn, self.slabs))
+
+    def _rows(self, s):
+        return slice(s.row_offset, s.row_offset + s.local_height)
+
+    def close(self):
+        self._each(lambda s: s.close())
+        self._pool.shutdown()
+
+    def halo_mode(self):
+        return self.slabs[0].halo_mode() if len(self.slabs) > 1 else "none"
+
+    def init_equilibrium(self, rho, vx, vy):
+        for s in self.slabs:
+            s.init_equilibrium(rho[self._rows(s)], vx[self._rows(s)], vy[self._rows(s)])
+
+    @property
+    def geometry(self):
+        return np.concatenate([s.geometry for s in self.slabs], axis=0)
+
+    @geometry.setter
+    def geometry(self, solid):
+        solid = np.asarray(solid).reshape(self.global_height, self.width)
+        for s in self.slabs:
+            s.geometry = solid[self._rows(s)]
+
+    def step(self, nsteps: int = 1):
+        self._each(lambda s: s.step(nsteps))
+
+    def synchronize(self):
+        self._each(lambda s: s.synchronize())
+
+    @property
+    def time(self):
+        return self.slabs[0].time
+
+    def size(self):
+        return (self.width, self.global_height)
+
+    def _cat(self, getter):
+        return Matrix(np.concatenate([getter(s).array for s in self.slabs], axis=0))
+
+    def _cat2(self, getter):
+        parts = [getter(s) for s in self.slabs]
+        return (Matrix(np.concatenate([p[0].array for p in parts], axis=0)),
+                Matrix(np.concatenate([p[1].array for p in parts], axis=0)))
+
+    def density(self):
+        return self._cat(lambda s: s.density())
+
+    def pressure(self):
+        return self._cat(lambda s: s.pressure())
+
+    def speed(self):
+        return self._cat(lambda s: s.speed())
+
+    def velocity(self):
+        return self._cat2(lambda s: s.velocity())
+
+    def momentum_density(self):
+        return self._cat2(lambda s: s.momentum_density())
+
+    def population(self, q):
+        return self._cat(lambda s: s.population(q))
+
+    def populations_array(self):
+        return np.concatenate([s.populations_array() for s in self.slabs], axis=1)
+
+    def is_unstable(self):
+        return any(s.is_unstable() for s in self.slabs)
+
+    def total_mass(self):
+        return float(sum(s.total_mass() for s in self.slabs))
+
+    def render(self, mode=0, overlay_geometry=True):
+        return np.concatenate(self._each(lambda s: s.render(mode, overlay_geometry)), axis=0)
+
+    def kernel_launches(self):
+        return sum(s.kernel_launches() for s in self.slabs)

@@ -39,3 +39,31 @@ def test_sharded_equals_unsharded(w, hg, edge, dtype):
 def test_sharded_with_fused_peer_memory_halo_equals_unsharded(w, hg, edge, dtype):
     """The face kernel stores the halo into the neighbours' ghost rows itself (cudaIpc + NVLink)."""
     run_worker(w, hg, edge, dtype, "p2p")
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+def test_single_process_multi_gpu_state(p2p):
+    """lbm.MultiState: one process, one host thread per GPU, same-process peer mapping."""
+    import numpy as np
+    from chemsim_b200 import lbm, scenarios
+    from oracle import lbm_oracle as O
+    world = min(n_gpus(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    dtype = np.float32
+    w, h = 2048, 64 * world + 3
+    rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=77, solid_fraction=0.02)
+    multi = lbm.MultiState((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC, devices=range(world), p2p=p2p)
+    assert multi.halo_mode() == ("p2p" if p2p else "nccl")
+    multi.init_equilibrium(rho, vx, vy)
+    multi.geometry = solid
+    for n in (1, 2, 9):
+        multi.step(n)
+    multi.synchronize()
+    ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 12, 0.8, O.EDGE_PERIODIC)
+    got = multi.populations_array()
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+    np.testing.assert_array_equal(multi.density().array.view(np.uint32), O.density(ref).view(np.uint32))
+    assert abs(multi.total_mass() - O.total_mass(ref)) <= 1e-12 * O.total_mass(ref)
+    assert multi.render(1).shape == (h, w, 4)
+    multi.close()
