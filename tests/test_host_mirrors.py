@@ -66,3 +66,19 @@ def test_channel_scenario():
     rho, vx, vy, solid = scenarios.channel_cylinder(512, 128, np.float32, radius=8.0, cx=64.0)
     assert solid[0].all() and solid[-1].all() and solid[64, 64] and not solid[64, 80]
     assert (vy == np.float32(0.05)).all() and (vx == 0).all()
+
+
+def test_c_example_builds_and_fails_loudly_without_gpu(tmp_path):
+    build.build()
+    exe = tmp_path / "c_api_demo"
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_api_demo.c"), "-o", str(exe), "-L" + os.path.join(ROOT, "chemsim_b200"),
+           "-lchemsim_lbm", "-Wl,-rpath," + os.path.join(ROOT, "chemsim_b200"), "-lm"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    import torch
+    run = subprocess.run([str(exe), "64", "64", "2"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and run.stdout.count("frame") == 2
+    else:
+        assert run.returncode == 1 and "status 3" in run.stderr      # CHEMSIM_LBM_ERR_CUDA, no fallback
