@@ -101,17 +101,24 @@ class ClockSampler:
         except Exception:
             self._nv = None
 
-    def _run(self):
+    def sample_now(self):
+        """One sample, taken by the caller while the GPU is busy (guarantees at least one
+        sample under load even when the timed region is shorter than the sampling period)."""
         nv = self._nv
+        if not nv:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._dev, nv.NVML_CLOCK_SM))
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._dev)
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._dev, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._dev)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample_now()
             self._stop.wait(0.02)
 
     def __enter__(self):
@@ -276,6 +283,7 @@ def run_gpu_arm(args):
         ev0.record(stream)
         state.step(args.steps)
         ev1.record(stream)
+        clocks.sample_now()              # the steps are queued and running: a sample under load
         state.synchronize()
         barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
