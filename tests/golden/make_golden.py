@@ -43,6 +43,9 @@ def main():
         rho, vx, vy, solid = scenarios.main_rs(48, 48, dtype, walls=True, radius=6.0)
         for s, f in run(rho, vx, vy, solid, dtype, ("bgk", 15.0), False, (1, 2, 10)).items():
             cases[f"mainrs48_zerofill_bgk15_{tag}_n{s}"] = f
+        # main.rs's ACTIVE configuration: Regularized<KBC> (src/main.rs:198-199), literal zero-fill edges
+        for s, f in run(rho, vx, vy, solid, dtype, ("regularized",), False, (1, 2, 10)).items():
+            cases[f"mainrs48_zerofill_regularized_{tag}_n{s}"] = f
         rho, vx, vy, solid = scenarios.main_rs(48, 48, dtype, walls=False, radius=6.0)
         for s, f in run(rho, vx, vy, solid, dtype, ("bgk", 15.0), True, (1, 25)).items():
             cases[f"mainrs48_periodic_bgk15_{tag}_n{s}"] = f

@@ -13,7 +13,9 @@ from oracle import lbm_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "d2q9_golden.npz"))
+import golden_cases  # noqa: E402
+
+GOLDEN = golden_cases.GOLDEN
 DTYPES = [np.float32, np.float64]
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
 
@@ -90,25 +92,17 @@ def test_config1_stable_twin_periodic_1000_steps(dtype):
     assert not state.is_unstable()
 
 
-def golden_bgk_cases():
-    for name in GOLDEN.files:
-        if "_bgk" in name:
-            yield name
-
-
-@pytest.mark.parametrize("name", list(golden_bgk_cases()))
+@pytest.mark.parametrize("name", golden_cases.names())
 def test_golden_vectors(name):
-    dtype = np.float32 if "float32" in name else np.float64
-    n = int(name.split("_")[-1][1:])
-    if name.startswith("mainrs48_zerofill"):
-        (rho, vx, vy, solid), edge, tau = scenarios.main_rs(48, 48, dtype, True, 6.0), lbm.EDGE_ZEROFILL, 15.0
-    elif name.startswith("mainrs48_periodic"):
-        (rho, vx, vy, solid), edge, tau = scenarios.main_rs(48, 48, dtype, False, 6.0), lbm.EDGE_PERIODIC, 15.0
-    else:
-        edge = lbm.EDGE_PERIODIC if "_periodic_" in name else lbm.EDGE_ZEROFILL
-        (rho, vx, vy, solid), tau = scenarios.random_state(40, 24, dtype, seed=7), 0.8
-    state = make_state(rho, vx, vy, solid, tau, edge, dtype)
-    state.step(n)
+    case = golden_cases.parse(name)
+    dtype = case["dtype"]
+    rho, vx, vy, solid = case["inputs"]
+    h, w = rho.shape
+    m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
+    disc = lbm.Discretization(1.0, 1.0)
+    pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
+    state = lbm.State.initial(lbm.D2Q9.new(pops), solid, case["mirror_collision"], disc, edge=case["edge"])
+    state.step(case["steps"])
     assert_parity(state.populations_array(), GOLDEN[name], name)
 
 
@@ -376,23 +370,6 @@ def test_other_collision_operators_match_oracle(name, edge, dtype):
         assert np.isfinite(f_ref).all()
         assert_parity(state.populations_array(), f_ref, f"{name} {w}x{h}")
         state.close()
-
-
-@pytest.mark.parametrize("name", [n for n in GOLDEN.files if "_bgk" not in n])
-def test_golden_vectors_other_operators(name):
-    dtype = np.float32 if "float32" in name else np.float64
-    n = int(name.split("_")[-1][1:])
-    kind = name.split("_")[2]
-    op = {"trt": lbm.TRT(tau_minus=1.1, tau_plus=0.8), "regularized": lbm.Regularized.new(lbm.KBC.new(10.0)),
-          "kbc": lbm.KBC.new(0.1)}[kind]
-    rho, vx, vy, solid = scenarios.random_state(40, 24, dtype, seed=7)
-    h, w = rho.shape
-    m = lambda a: lbm.Matrix.new(a.reshape(-1), (w, h), dtype=dtype)
-    disc = lbm.Discretization(1.0, 1.0)
-    pops = lbm.compute_equilibrium(m(rho), (m(vx), m(vy)), lbm.D2Q9.directions(), disc)
-    state = lbm.State.initial(lbm.D2Q9.new(pops), solid, op, disc, edge=lbm.EDGE_PERIODIC)
-    state.step(n)
-    assert_parity(state.populations_array(), GOLDEN[name], name)
 
 
 def test_main_rs_active_configuration_regularized_kbc_400():

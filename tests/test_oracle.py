@@ -10,7 +10,9 @@ from chemsim_b200 import scenarios
 from oracle import lbm_numpy as N
 from oracle import lbm_oracle as O
 
-GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "d2q9_golden.npz"))
+import golden_cases  # noqa: E402  (tests/ is on sys.path under pytest's rootdir conftest)
+
+GOLDEN = golden_cases.GOLDEN
 DTYPES = [np.float32, np.float64]
 
 
@@ -136,32 +138,13 @@ def test_fused_equals_three_pass_bitwise(dtype, edge):
     assert_bit_equal(a, b)
 
 
-def _golden_inputs(name, dtype):
-    if name.startswith("mainrs48_zerofill"):
-        return scenarios.main_rs(48, 48, dtype, walls=True, radius=6.0), O.EDGE_ZEROFILL
-    if name.startswith("mainrs48_periodic"):
-        return scenarios.main_rs(48, 48, dtype, walls=False, radius=6.0), O.EDGE_PERIODIC
-    edge = O.EDGE_PERIODIC if "_periodic_" in name else O.EDGE_ZEROFILL
-    return scenarios.random_state(40, 24, dtype, seed=7), edge
-
-
-def golden_cases():
-    for name in GOLDEN.files:
-        parts = name.split("_")
-        dtype = np.float32 if "float32" in parts else np.float64
-        n = int(parts[-1][1:])
-        colname = parts[2]
-        col = {"bgk15": O.collision(O.BGK, tau=15.0), "bgk08": O.collision(O.BGK, tau=0.8),
-               "trt": O.collision(O.TRT, tau_plus=0.8, tau_minus=1.1),
-               "regularized": O.collision(O.REGULARIZED), "kbc": O.collision(O.KBC, viscosity=0.1)}[colname]
-        yield name, dtype, n, col
-
-
-@pytest.mark.parametrize("name,dtype,n,col", list(golden_cases()), ids=[c[0] for c in golden_cases()])
-def test_c_oracle_reproduces_golden_vectors(name, dtype, n, col):
-    (rho, vx, vy, solid), edge = _golden_inputs(name, dtype)
-    f = O.step_ref(O.compute_equilibrium(rho, vx, vy), solid, n, col, edge)
+@pytest.mark.parametrize("name", golden_cases.names())
+def test_c_oracle_reproduces_golden_vectors(name):
+    case = golden_cases.parse(name)
+    rho, vx, vy, solid = case["inputs"]
+    f = O.step_ref(O.compute_equilibrium(rho, vx, vy), solid, case["steps"], case["oracle_collision"], case["edge"])
     assert_bit_equal(f, GOLDEN[name])
+    assert case["mirror_collision"] is not None        # the host mirror's operator object builds on CPU
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
