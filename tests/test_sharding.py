@@ -58,3 +58,81 @@ def test_gloo_emulation_matches_unsharded_oracle(world, w, hg, edge, dtype):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "SHARD_OK" in res.stdout
+
+
+@pytest.mark.parametrize("world,edge", [(2, _ffi.EDGE_PERIODIC), (3, _ffi.EDGE_PERIODIC), (4, _ffi.EDGE_ZEROFILL)])
+def test_peer_memory_flag_protocol_model(world, edge):
+    """Executable model of the fused peer-memory halo: ranks are threads, "peer
+    memory" is shared numpy storage, the arithmetic is the oracle's slab step.  Each rank waits
+    until both neighbours have published step t, updates its slab from buffer t%2 into (t+1)%2,
+    stores its outgoing face populations into the NEIGHBOURS' ghost rows of (t+1)%2 and then
+    publishes t+1.  Random delays shake the interleavings; the invariant under test is that the
+    A-B buffers plus one step counter per face are enough (a neighbour is never more than one
+    step ahead), i.e. the result equals the unsharded run bit for bit and nothing deadlocks."""
+    import threading
+    import time
+
+    import numpy as np
+
+    from chemsim_b200 import scenarios
+    from oracle import lbm_oracle as O
+
+    dtype, w, hg, steps = np.float32, 16, 4 * world + 1, 25
+    rho, vx, vy, solid = scenarios.random_state(w, hg, dtype, seed=5)
+    f0 = O.compute_equilibrium(rho, vx, vy)
+    slabs = [lbm.slab_rows(hg, r, world) for r in range(world)]
+    periodic = edge == _ffi.EDGE_PERIODIC
+    up = [(r - 1) % world if (periodic or r > 0) else None for r in range(world)]
+    down = [(r + 1) % world if (periodic or r < world - 1) else None for r in range(world)]
+    bufs = []                                   # bufs[r][parity] : (9, h+2, w) with ghost rows
+    for r0, h in slabs:
+        a = np.zeros((9, h + 2, w), dtype)
+        a[:, 1:h + 1] = f0[:, r0:r0 + h]
+        bufs.append([a, np.zeros_like(a)])
+    # the first exchange (NCCL in the product): ghost rows of buffer 0
+    for r, (r0, h) in enumerate(slabs):
+        if up[r] is not None:
+            bufs[r][0][[3, 6, 7], 0] = bufs[up[r]][0][[3, 6, 7], slabs[up[r]][1]]
+        if down[r] is not None:
+            bufs[r][0][[1, 5, 8], h + 1] = bufs[down[r]][0][[1, 5, 8], 1]
+    flags = np.zeros((world, 2), dtype=np.int64)      # [rank][0: from_up, 1: from_down], "step published"
+    cond = threading.Condition()
+    rng = np.random.default_rng(world)
+    delays = rng.random((world, steps)) * 2e-3
+    errors = []
+
+    def rank(r):
+        r0, h = slabs[r]
+        try:
+            for t in range(steps):
+                with cond:                      # wait_flag: both neighbours have published step t
+                    ok = cond.wait_for(lambda: (up[r] is None or flags[r, 0] >= t) and
+                                       (down[r] is None or flags[r, 1] >= t), timeout=20)
+                    assert ok, f"rank {r} timed out at step {t}"
+                time.sleep(delays[r, t])
+                src, dst = bufs[r][t % 2], bufs[r][(t + 1) % 2]
+                O.step_fused_slab(src, dst, np.ascontiguousarray(solid[r0:r0 + h]), edge, 0.8)
+                if down[r] is not None:         # dy=+1 movers -> lower neighbour's ghost row -1
+                    bufs[down[r]][(t + 1) % 2][[3, 6, 7], 0] = dst[[3, 6, 7], h]
+                if up[r] is not None:           # dy=-1 movers -> upper neighbour's ghost row H_up
+                    bufs[up[r]][(t + 1) % 2][[1, 5, 8], slabs[up[r]][1] + 1] = dst[[1, 5, 8], 1]
+                with cond:                      # publish t+1 (after the stores)
+                    if down[r] is not None:
+                        flags[down[r], 0] = t + 1
+                    if up[r] is not None:
+                        flags[up[r], 1] = t + 1
+                    cond.notify_all()
+        except Exception as e:                  # pragma: no cover
+            errors.append(e)
+            with cond:
+                cond.notify_all()
+
+    threads = [threading.Thread(target=rank, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(60)
+    assert not errors, errors
+    got = np.concatenate([bufs[r][steps % 2][:, 1:slabs[r][1] + 1] for r in range(world)], axis=1)
+    ref = O.step_fused(f0, solid, steps, 0.8, edge)
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
