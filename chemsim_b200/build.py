@@ -94,7 +94,26 @@ def build_harness(force: bool = False) -> str:
     return HARNESS
 
 
+MULTI_HARNESS = os.path.join(HERE, "cpp", "multi_gpu_harness")
+
+
+def build_multi_harness(force: bool = False) -> str:
+    """Single-process multi-GPU driver (cpp/lbm_multi.hpp + cpp/multi_gpu_harness.cpp)."""
+    build()
+    src = [os.path.join(HERE, "cpp", n) for n in ("multi_gpu_harness.cpp", "lbm_multi.hpp", "lbm.hpp")]
+    if not force and os.path.exists(MULTI_HARNESS) and all(
+            os.path.getmtime(s) < os.path.getmtime(MULTI_HARNESS) for s in src + [LIB]):
+        return MULTI_HARNESS
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-o", MULTI_HARNESS, src[0],
+           "-L" + HERE, "-lchemsim_lbm", "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return MULTI_HARNESS
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print(LIB)
     print(build_harness(force="--force" in sys.argv))
+    print(build_multi_harness(force="--force" in sys.argv))

@@ -67,3 +67,33 @@ def test_single_process_multi_gpu_state(p2p):
     assert abs(multi.total_mass() - O.total_mass(ref)) <= 1e-12 * O.total_mass(ref)
     assert multi.render(1).shape == (h, w, 4)
     multi.close()
+
+
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_cpp_single_process_multi_gpu_driver(halo):
+    """chemsim_b200/cpp/lbm_multi.hpp: main.rs's scenario on all GPUs from one process (one host
+    thread per slab), frame by frame against the oracle."""
+    import re
+    import numpy as np
+    from chemsim_b200 import build, scenarios
+    from oracle import lbm_oracle as O
+    world = min(n_gpus(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    exe = build.build_multi_harness()
+    w, h, frames = 1024, 40 * world + 1, 5
+    res = subprocess.run([exe, str(w), str(h), str(frames), str(world), halo], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert f"halo {halo}" in res.stdout
+    lines = [l for l in res.stdout.splitlines() if l.startswith("frame")]
+    assert len(lines) == frames
+    rho, vx, vy, solid = scenarios.main_rs(w, h, np.float32)
+    f = O.compute_equilibrium(rho, vx, vy)
+    col = O.collision(O.BGK, tau=15.0)
+    for i, line in enumerate(lines):
+        f = O.step_ref(f, solid, 2, col, O.EDGE_ZEROFILL)
+        m = re.match(r"frame (\d+) time (\S+) mass (\S+) rho (\S+) unstable (\d)", line)
+        assert int(m.group(1)) == i and float(m.group(2)) == 2.0 * (i + 1)
+        assert abs(float(m.group(3)) - O.total_mass(f)) <= 1e-12 * O.total_mass(f)
+        assert np.float32(m.group(4)) == O.density(f)[h // 2, w // 4]
+        assert int(m.group(5)) == int(O.is_unstable(f))
