@@ -167,9 +167,31 @@ def cpu_baseline(w, dtype_name, budget_s=25.0):
     steps = int(max(5, min(20000, budget_s / max(t5, 1e-4))))
     dt = cpu_time_steps(w, rows, dtype, steps, 3)
     glups = w * rows * steps / dt / 1e9
-    return {"value": glups, "unit": "GLUPS", "cores": O.max_threads(), "kind": "port",
-            "sample": f"{w}x{rows} band of the workload, periodic, {steps} steps, fused OpenMP restatement of lbm.rs "
-                      f"(oracle/lbm_oracle.c, not ArrayFire), {dt:.2f} s"}
+    out = {"value": glups, "unit": "GLUPS", "cores": O.max_threads(), "kind": "port",
+           "sample": f"{w}x{rows} band of the workload, periodic, {steps} steps, fused OpenMP restatement of lbm.rs "
+                     f"(oracle/lbm_oracle.c, not ArrayFire), {dt:.2f} s"}
+    try:
+        out["reference_structured_1thread"] = cpu_reference_structured(dtype)
+    except Exception as e:                      # informational only
+        out["reference_structured_1thread"] = {"error": str(e)}
+    return out
+
+
+def cpu_reference_structured(dtype, size=1024, steps=3):
+    """The oracle in the reference's own structure: three separate passes
+    (stream / bounce-back / collide) with full-array temporaries, single thread, mirroring
+    lbm.rs's array-at-a-time calls.  Informational: what the restatement costs before fusing."""
+    from chemsim_b200 import scenarios
+    from oracle import lbm_oracle as O
+    rho, vx, vy, solid = scenarios.smooth_periodic(size, size, dtype)
+    f = O.compute_equilibrium(rho, vx, vy)
+    col = O.collision(O.BGK, tau=TAU)
+    f = O.step_ref(f, solid, 1, col, O.EDGE_PERIODIC)
+    t0 = time.perf_counter()
+    f = O.step_ref(f, solid, steps, col, O.EDGE_PERIODIC)
+    dt = time.perf_counter() - t0
+    return {"value": size * size * steps / dt / 1e9, "unit": "GLUPS", "cores": 1,
+            "sample": f"{size}x{size}, {steps} steps, three-pass array-at-a-time restatement"}
 
 
 def run_reference_arm(args):
