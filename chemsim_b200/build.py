@@ -15,8 +15,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchemsim_lbm.so")
-SOURCES = ["kernels.cu", "lattice.cu"]
-HEADERS = ["d2q9.cuh", "kernels.cuh", "nccl_dyn.h", os.path.join("..", "..", "include", "chemsim_lbm.h")]
+# one translation unit per collision operator for the fused step kernels (compiled in parallel)
+SOURCES = ["step_bgk.cu", "step_trt.cu", "step_regularized.cu", "step_kbc.cu", "kernels.cu", "lattice.cu"]
+HEADERS = ["d2q9.cuh", "consts.hpp", "kernels.cuh", "step_decl.cuh", "step_impl.cuh", "nccl_dyn.h",
+           os.path.join("..", "..", "include", "chemsim_lbm.h")]
+OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -24,9 +27,8 @@ NVCC_FLAGS = [
     "-fmad=false",                      # parity build: never contract a*b+c (d2q9.cuh also uses *_rn intrinsics)
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
     "-Xptxas", "-v",
-    "-cudart", "static",
-    "-shared",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared"]
 
 
 def nvcc() -> str:
@@ -44,36 +46,54 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_and_link(out: str, defines: list[str], log_path: str, tag: str) -> None:
+    """nvcc -c every translation unit in parallel (one process each), then link the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    env = dict(os.environ)
+    env["PATH"] = "/usr/bin:" + env.get("PATH", "")     # plain system g++ as nvcc's host compiler
+    objdir = os.path.join(OBJ_DIR, tag)
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src: str):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-ccbin", "g++", "-c", "-o", obj,
+               os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        return obj, cmd, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = ""
+    for obj, cmd, res in results:
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+    failed = [r for r in results if r[2].returncode != 0]
+    if not failed:
+        cmd = [nvcc(), *LINK_FLAGS, "-ccbin", "g++", "-o", out, *[r[0] for r in results], "-ldl"]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        if res.returncode != 0:
+            failed = [(out, cmd, res)]
+    with open(log_path, "w") as fh:
+        fh.write(log)
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(r[2].stdout + r[2].stderr for r in failed))
+
+
 def build_variant(name: str, defines: list[str]) -> str:
     """Experimental build with extra -D switches -> chemsim_b200/libchemsim_lbm_<name>.so
-    (select at run time with CHEMSIM_LBM_LIB=<path>; used by tools/variants.sh)."""
+    (select at run time with CHEMSIM_LBM_LIB=<path>; used by tools/variants.py)."""
     out = os.path.join(HERE, f"libchemsim_lbm_{name}.so")
-    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-ccbin", "g++", "-o", out,
-           *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
-    env = dict(os.environ)
-    env["PATH"] = "/usr/bin:" + env.get("PATH", "")
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    with open(os.path.join(HERE, f"build_{name}.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    _compile_and_link(out, defines, os.path.join(HERE, f"build_{name}.log"), name)
     return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", "g++", "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
-    env = dict(os.environ)
-    env["PATH"] = "/usr/bin:" + env.get("PATH", "")     # plain system g++ as nvcc's host compiler
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log)
+    _compile_and_link(LIB, [], os.path.join(HERE, "build.log"), "default")
     if verbose:
-        print(log)
+        with open(os.path.join(HERE, "build.log")) as fh:
+            print(fh.read())
     return LIB
 
 

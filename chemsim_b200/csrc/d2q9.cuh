@@ -120,17 +120,74 @@ __device__ __forceinline__ T equilibrium_i(int i, T rho, T vx, T vy, T v2, const
     return mul(mul(rho, k.w[i]), sum);
 }
 
+// ---- the step kernels' form of the same arithmetic ----------------------------------
+// The functions above evaluate the reference's expression tree literally (every product by
+// 0 and +-1 formed); they serve the readouts and the initialisation, whose outputs ARE those
+// intermediate values.  The collision operators below only have to produce the same nine
+// post-collision populations, so they drop operations that provably cannot change them.
+// Every identity used is exact in IEEE-754 round-to-nearest for FINITE inputs:
+//   (1) x*(+1) == x;  x*(-1) == -x;  a + (-x) == a - x;  RN(-z) == -RN(z)
+//   (2) x*0 == +-0, and acc + (+-0) == acc whenever acc is not -0.  An accumulator that starts
+//       as (+0) + y is never -0 (x + y == -0 only if x == y == -0), so the zero terms of
+//       momentum_density / the Pi_neq sums vanish bit for bit.
+//   (3) 1 + (+-0) == 1: the sign of a zero velocity component never reaches the equilibrium
+//       (vc enters it only through 1 + vc*k1 and vc*vc).
+//   (4) equal operands give equal results: w_1..w_4 and w_5..w_8 are the same number
+//       (4/36, 1/36, make_consts), vc_opp(i) == -vc_i, so a_i = vc_i*k1 and b_i = vc_i^2*k2 are
+//       shared by a direction and its opposite: sum_i = ((1 + a) + b) + c, sum_opp = ((1 - a) + b) + c.
+// Not preserved: which of inf/NaN appears once a population has overflowed (the literal tree
+// turns inf*0 into NaN earlier), and, for Regularized only, the SIGN of an exactly-zero result
+// when an equilibrium underflows to -0.  tests/ compare these kernels bit for bit with the
+// literal oracle; tools/config1_divergence.py follows the blow-up of config 1.
+
+// Lattice::density + momentum_density + velocity (src/lbm.rs:117-138) by identities (1), (2).
+template <typename T>
+__device__ __forceinline__ Moments<T> moments_reduced(const T (&g)[Q])
+{
+    Moments<T> m;
+    m.rho = density(g);
+    // c_x = (0, 1, 0,-1, 0, 1,-1,-1, 1):  ((0 + g1) - g3) + g5 - g6 - g7 + g8, in index order
+    m.mx = add(sub(sub(add(sub(add(T(0), g[1]), g[3]), g[5]), g[6]), g[7]), g[8]);
+    // c_y = (0, 0, 1, 0,-1, 1, 1,-1,-1):  ((0 + g2) - g4) + g5 + g6 - g7 - g8
+    m.my = sub(sub(add(add(sub(add(T(0), g[2]), g[4]), g[5]), g[6]), g[7]), g[8]);
+    const T r = recip(m.rho);
+    m.vx = mul(r, m.mx);
+    m.vy = mul(r, m.my);
+    return m;
+}
+
+// compute_equilibrium for all nine directions (src/lbm.rs:58-68) by identities (1), (3), (4).
+template <typename T>
+__device__ __forceinline__ void equilibrium_pair(T vc, T c, T rw, const Consts<T> &k, T &fe_i, T &fe_opp)
+{
+    const T a = mul(vc, k.k1);
+    const T b = mul(mul(vc, vc), k.k2);
+    fe_i   = mul(rw, add(add(add(T(1), a), b), c));
+    fe_opp = mul(rw, add(add(sub(T(1), a), b), c));     // vc_opp = -vc: 1 + (-a) == 1 - a
+}
+
+template <typename T>
+__device__ __forceinline__ void equilibrium_all(const T (&g)[Q], const Consts<T> &k, Moments<T> &m, T (&fe)[Q])
+{
+    m = moments_reduced(g);
+    const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));   // src/lbm.rs:53
+    const T c = mul(v2, k.k3);
+    const T rw0 = mul(m.rho, k.w[0]), rws = mul(m.rho, k.w[1]), rwd = mul(m.rho, k.w[5]);
+    fe[0] = mul(rw0, add(T(1), c));                       // vc_0 = +-0: ((1 + +-0) + 0) + c
+    equilibrium_pair(m.vx, c, rws, k, fe[1], fe[3]);                 // c_1 = ( 1, 0) = -c_3
+    equilibrium_pair(m.vy, c, rws, k, fe[2], fe[4]);                 // c_2 = ( 0, 1) = -c_4
+    equilibrium_pair(add(m.vx, m.vy), c, rwd, k, fe[5], fe[7]);      // c_5 = ( 1, 1) = -c_7
+    equilibrium_pair(sub(m.vy, m.vx), c, rwd, k, fe[6], fe[8]);      // c_6 = (-1, 1) = -c_8
+}
+
 // State::collide with BGK (src/lbm.rs:731-739, :349-364): g <- g + (g - feq)*factor
 template <typename T>
 __device__ __forceinline__ void collide_bgk(T (&g)[Q], const Consts<T> &k)
 {
-    const Moments<T> m = moments(g);
-    const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));   // src/lbm.rs:53
+    Moments<T> m; T fe[Q];
+    equilibrium_all(g, k, m, fe);
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const T fe = equilibrium_i(i, m.rho, m.vx, m.vy, v2, k);
-        g[i] = add(g[i], mul(sub(g[i], fe), k.factor));
-    }
+    for (int i = 0; i < Q; ++i) g[i] = add(g[i], mul(sub(g[i], fe[i]), k.factor));
 }
 
 // ---- the other CollisionOperator impls of src/lbm.rs ---------------------------
@@ -145,15 +202,6 @@ struct Num {
     __device__ __forceinline__ Num operator*(Num o) const { return Num(mul(v, o.v)); }
     __device__ __forceinline__ Num operator/(Num o) const { return Num(divi(v, o.v)); }
 };
-
-template <typename T>
-__device__ __forceinline__ void equilibrium_all(const T (&g)[Q], const Consts<T> &k, Moments<T> &m, T (&fe)[Q])
-{
-    m = moments(g);
-    const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));
-#pragma unroll
-    for (int i = 0; i < Q; ++i) fe[i] = equilibrium_i(i, m.rho, m.vx, m.vy, v2, k);
-}
 
 // TRT::evaluate (src/lbm.rs:401-444).  swap_equilibrium (:311-322) overwrites slots
 // 1..8 of the equilibrium with the opposite *population* — reproduced as written.
@@ -176,30 +224,33 @@ __device__ __forceinline__ void collide_trt(T (&g)[Q], const Consts<T> &k)
 }
 
 // Regularized::evaluate (src/lbm.rs:606-661); never calls the underlying operator.
+// Pi_neq (:625-632) by identities (1), (2): c_x^2, c_y^2 are 0/1 and c_x*c_y is 0/+-1, and the
+// yx sum repeats the xy sum operand for operand.  The second loop (:647-658) shares its products
+// between directions of equal (c^2, w) (identity (4): axx_1 == axx_3, axx_5..8 equal, axy_6 ==
+// -axy_5, ...) and skips the +-0 terms of the axis directions.
 template <typename T>
 __device__ __forceinline__ void collide_regularized(T (&g)[Q], const Consts<T> &k)
 {
-    using N = Num<T>;
     Moments<T> m; T fe[Q];
     equilibrium_all(g, k, m, fe);
-    N sxx(T(0)), sxy(T(0)), syx(T(0)), syy(T(0));
+    T n[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {                       // :625-632
-        const N fneq = N(g[i]) - N(fe[i]);
-        sxx = sxx + fneq * N(T(cx_of(i) * cx_of(i)));
-        sxy = sxy + fneq * N(T(cx_of(i) * cy_of(i)));
-        syx = syx + fneq * N(T(cy_of(i) * cx_of(i)));
-        syy = syy + fneq * N(T(cy_of(i) * cy_of(i)));
-    }
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {                       // :647-658
-        N reg(fe[i]);
-        reg = reg + sxx * N(k.axx[i]);
-        reg = reg + sxy * N(k.axy[i]);
-        reg = reg + syx * N(k.ayx[i]);
-        reg = reg + syy * N(k.ayy[i]);
-        g[i] = reg.v;
-    }
+    for (int i = 0; i < Q; ++i) n[i] = sub(g[i], fe[i]);
+    const T sxx = add(add(add(add(add(add(T(0), n[1]), n[3]), n[5]), n[6]), n[7]), n[8]);
+    const T syy = add(add(add(add(add(add(T(0), n[2]), n[4]), n[5]), n[6]), n[7]), n[8]);
+    const T sxy = sub(add(sub(add(T(0), n[5]), n[6]), n[7]), n[8]);     // == syx
+    const T xx0 = mul(sxx, k.axx[0]), xx1 = mul(sxx, k.axx[1]), xx2 = mul(sxx, k.axx[2]), xx5 = mul(sxx, k.axx[5]);
+    const T yy0 = mul(syy, k.ayy[0]), yy1 = mul(syy, k.ayy[1]), yy2 = mul(syy, k.ayy[2]), yy5 = mul(syy, k.ayy[5]);
+    const T xy5 = mul(sxy, k.axy[5]);                                   // axy_7 = axy_5, axy_6 = axy_8 = -axy_5
+    g[0] = add(add(fe[0], xx0), yy0);
+    g[1] = add(add(fe[1], xx1), yy1);
+    g[2] = add(add(fe[2], xx2), yy2);
+    g[3] = add(add(fe[3], xx1), yy1);
+    g[4] = add(add(fe[4], xx2), yy2);
+    g[5] = add(add(add(add(fe[5], xx5), xy5), xy5), yy5);
+    g[6] = add(sub(sub(add(fe[6], xx5), xy5), xy5), yy5);
+    g[7] = add(add(add(add(fe[7], xx5), xy5), xy5), yy5);
+    g[8] = add(sub(sub(add(fe[8], xx5), xy5), xy5), yy5);
 }
 
 // KBC::evaluate (src/lbm.rs:468-585), entropic stabiliser gamma*.

@@ -1,358 +1,16 @@
-// kernels.cu — sm_100a kernels of the D2Q9 path.
+// kernels.cu — sm_100a kernels of the D2Q9 path other than the fused step itself, and the
+// dispatch of the step launchers.
 //
-//  step_vec_kernel     the hot path: ONE pass per time step that pull-streams the
-//                      nine populations (State::stream, src/lbm.rs:716-729),
-//                      reverses them on solid cells (State::bounce_back, :741-751)
-//                      and relaxes them (State::collide + BGK, :731-739, :349-364),
-//                      with 128-bit loads/stores over the SoA layout.
-//  step_scalar_kernel  the same update, one cell per thread, for widths that are
-//                      not a multiple of the vector width.
-//  readout / mass / unstable / init kernels for the macroscopic surface of
-//                      lbm.rs (:117-160, :779-818, :43-71).
-//
-// HBM-bound integer-free streaming work: no tensor cores, no shared-memory
-// tiling (every population value is read once and written once per step).
-#include "kernels.cuh"
-
-#include <cstdlib>
+//  The step kernels (step_vec_kernel, step_slab_p2p_kernel, step_face_p2p_kernel,
+//  step_scalar_kernel) live in step_impl.cuh and are instantiated per collision operator in
+//  step_bgk.cu / step_trt.cu / step_regularized.cu / step_kbc.cu.
+//  Here: readout / mass / unstable / init kernels for the macroscopic surface of lbm.rs
+//  (:117-160, :779-818, :43-71), the segment flags of the geometry mask, the device-side render.
+#include "step_decl.cuh"
 
 namespace chemsim {
 
 namespace {
-
-template <typename T> struct VecOf;
-template <> struct VecOf<float>  { using type = float4;  static constexpr int N = 4; };
-template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
-
-#ifdef CHEMSIM_LOAD_NOALLOC
-#define CHEMSIM_LD_HINT ".L1::no_allocate"
-#else
-#define CHEMSIM_LD_HINT ""
-#endif
-
-// Predicated, branch-free global loads.  NC=true takes the read-only path: the
-// source buffer is never written by the kernel that reads it (A-B buffering), so
-// .nc is legal.  NC=false (coherent) is used by the P2P face kernel, whose ghost
-// rows are written by the neighbouring GPU while the kernel may already be resident.
-// Predication instead of `if` keeps every load of a thread in ONE straight-line
-// batch: all of them are in flight before the first use.  The asm statements carry no
-// memory dependence of their own: what keeps them behind griddepcontrol.wait and the halo
-// flag wait is a data dependence — every address is derived from an "order token" (always
-// 0, but opaque to the compiler) that those waits produce (see order_after_*).
-#define CHEMSIM_LDG_BODY(NCSTR)                                                                       \
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"                                             \
-        "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"                    \
-        "@q ld.global" NCSTR ".v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"                                   \
-        : "=&f"(v[0]), "=&f"(v[1]), "=&f"(v[2]), "=&f"(v[3]) : "l"(p), "r"((int)pred))
-template <bool NC>
-__device__ __forceinline__ void ldg_vec(const float *p, bool pred, float (&v)[4])
-{
-    if (NC) CHEMSIM_LDG_BODY(".nc" CHEMSIM_LD_HINT); else CHEMSIM_LDG_BODY("");
-}
-#undef CHEMSIM_LDG_BODY
-#define CHEMSIM_LDG_BODY(NCSTR)                                                                       \
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"                                             \
-        "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"                                                        \
-        "@q ld.global" NCSTR ".v2.f64 {%0, %1}, [%2];\n\t}"                                           \
-        : "=&d"(v[0]), "=&d"(v[1]) : "l"(p), "r"((int)pred))
-template <bool NC>
-__device__ __forceinline__ void ldg_vec(const double *p, bool pred, double (&v)[2])
-{
-    if (NC) CHEMSIM_LDG_BODY(".nc" CHEMSIM_LD_HINT); else CHEMSIM_LDG_BODY("");
-}
-#undef CHEMSIM_LDG_BODY
-template <bool NC>
-__device__ __forceinline__ float ldg_one(const float *p, bool pred)
-{
-    float v;
-    if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
-                : "=&f"(v) : "l"(p), "r"((int)pred));
-    else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.f32 %0, [%1];\n\t}"
-                : "=&f"(v) : "l"(p), "r"((int)pred));
-    return v;
-}
-template <bool NC>
-__device__ __forceinline__ double ldg_one(const double *p, bool pred)
-{
-    double v;
-    if (NC) asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
-                : "=&d"(v) : "l"(p), "r"((int)pred));
-    else    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b64 %0, 0;\n\t@q ld.global.f64 %0, [%1];\n\t}"
-                : "=&d"(v) : "l"(p), "r"((int)pred));
-    return v;
-}
-__device__ __forceinline__ void store_vec(float *p, const float (&v)[4])
-{
-#ifdef CHEMSIM_STORE_CS
-    __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
-#else
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-#endif
-}
-__device__ __forceinline__ void store_vec(double *p, const double (&v)[2])
-{
-#ifdef CHEMSIM_STORE_CS
-    __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
-#else
-    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
-#endif
-}
-// V mask bytes as one 32-/16-bit word (0 when !pred)
-__device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const float *)
-{
-    unsigned v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
-        : "=&r"(v) : "l"(p), "r"((int)pred));
-    return v;
-}
-__device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const double *)
-{
-    unsigned short v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b16 %0, 0;\n\t@q ld.global.nc.u16 %0, [%1];\n\t}"
-        : "=&h"(v) : "l"(p), "r"((int)pred));
-    return v;
-}
-
-// Build-time tunables (defaults are the measured best; tools/variants.py sweeps them).
-#ifndef CHEMSIM_STEP_THREADS
-#define CHEMSIM_STEP_THREADS 256
-#endif
-#ifndef CHEMSIM_STEP_MIN_BLOCKS
-#define CHEMSIM_STEP_MIN_BLOCKS 4   // <= 64 registers: 4 x 256 threads per SM (ptxas otherwise takes 88 for f64)
-#endif
-constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
-// resident blocks per SM the step kernels are compiled for: BGK fits 64 registers in both
-// precisions; the f64 TRT / Regularized bodies need ~80 (3 blocks), KBC is left unconstrained
-template <typename T, int COL>
-constexpr int step_min_blocks()
-{
-    return COL == COL_KBC ? 1 : (COL != COL_BGK && sizeof(T) == 8 ? 3 : CHEMSIM_STEP_MIN_BLOCKS);
-}
-
-// ---- the fused step, vector form ---------------------------------------------
-// Thread (tx, ty) of block (bx, by) updates the V = 16/sizeof(T) cells
-// x0 … x0+V−1 of row y.  blockDim.x is a multiple of 32, so a warp always lies
-// inside one row and the two neighbouring lanes hold the neighbouring vectors:
-// populations that stream along x (dx = ±1) are assembled from the thread's own
-// aligned vector plus ONE element shuffled in from the adjacent lane; only the
-// first/last lane of a warp (or of the row) issues an extra scalar load, which
-// also implements the x edge (wrap or zero-fill).
-// The update of V cells of row y by one thread (see the kernel comment above).
-// P2P=true additionally stores the populations that leave the slab through this face
-// row straight into the neighbouring GPU's ghost row (peer-mapped memory, NVLink).
-// griddepcontrol.wait as an opaque producer of 0: adding the result to a base pointer
-// orders every load derived from it after the wait.
-__device__ __forceinline__ int order_after_grid_dependency()
-{
-    int tok;
-    asm volatile("griddepcontrol.wait;\n\tmov.u32 %0, 0;" : "=r"(tok) : : "memory");
-    return tok;
-}
-
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool P2P>
-__device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y, const int xv, const int lane,
-                                              const int halo_tok)
-{
-    constexpr int V = VecOf<T>::N;
-    constexpr bool NC = !P2P;
-    const int nvec = a.W / V;
-    if (xv - lane >= nvec) return;                   // whole warp beyond the row
-    const bool active = xv < nvec;
-    const int x0 = xv * V;
-    // Programmatic dependent launch: the blocks of this step may already be resident while
-    // the previous kernel in the stream drains; nothing is read before it has completed and
-    // flushed (a no-op when the kernel was not launched as a dependent).  `tok` is 0.
-    const int tok = order_after_grid_dependency() + halo_tok;
-    const T *src = a.src + tok;
-    const uint8_t *mask = a.mask + tok, *mask_flags = a.mask_flags + tok;
-    // any solid cell in the 32*V cells of this warp?  (one or two 64-cell segments)
-    unsigned seg_flags = 0;
-    if (HAS_MASK) {
-        const uint8_t *fl = mask_flags + (size_t)y * a.flag_pitch + ((xv - lane) * V) / MASK_SEGMENT;
-        seg_flags = (V == 4) ? *reinterpret_cast<const unsigned short *>(fl) : *fl;
-    }
-    // which lanes must fetch the element their neighbour lane cannot supply
-    const bool first = xv == 0, last = xv == nvec - 1;
-    const bool need_left  = active && (lane == 0 || first)  && (PERIODIC_X || !first);
-    const bool need_right = active && (lane == 31 || last) && (PERIODIC_X || !last);
-    const int left_x  = first ? a.W - 1 : x0 - 1;    // wrap (periodic) or the previous warp's last element
-    const int right_x = last ? 0 : x0 + V;
-
-    // ---- phase 1: every load of this thread, back to back ----------------------
-    T v[Q][V];      // the aligned vector of each population's source row
-    T e[Q];         // the one extra element for populations that stream along x
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        int sy = y - ey_of(q);
-        if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
-        const T *row = src + (size_t)q * a.plane + (size_t)(sy + 1) * a.pitch;
-        ldg_vec<NC>(row + x0, active, v[q]);
-        if (ex_of(q) == 1)       e[q] = ldg_one<NC>(row + left_x, need_left);
-        else if (ex_of(q) == -1) e[q] = ldg_one<NC>(row + right_x, need_right);
-        else                     e[q] = T(0);
-    }
-    unsigned maskw = 0;
-    if (HAS_MASK && seg_flags != 0)                  // warp-uniform
-        maskw = ldg_mask(mask + (size_t)y * a.mask_pitch + x0, active, (const T *)nullptr);
-
-    // ---- phase 2: shift the x-streaming populations by one element -------------
-    T g[Q][V];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        if (ex_of(q) == 0) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) g[q][j] = v[q][j];
-        } else if (ex_of(q) == 1) {                  // value at x comes from x−1
-            const T nb = __shfl_up_sync(0xffffffffu, v[q][V - 1], 1);
-            g[q][0] = (lane == 0 || first) ? e[q] : nb;
-#pragma unroll
-            for (int j = 1; j < V; ++j) g[q][j] = v[q][j - 1];
-        } else {                                     // value at x comes from x+1
-            const T nb = __shfl_down_sync(0xffffffffu, v[q][0], 1);
-#pragma unroll
-            for (int j = 0; j < V - 1; ++j) g[q][j] = v[q][j + 1];
-            g[q][V - 1] = (lane == 31 || last) ? e[q] : nb;
-        }
-    }
-    if (!active) return;
-
-    // ---- phase 3: bounce-back + collide, cell by cell ---------------------------
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-        T c[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) c[q] = g[q][j];
-        if (HAS_MASK) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
-        collide<COL>(c, a.k);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) g[q][j] = c[q];
-    }
-
-    // ---- phase 4: nine aligned vector stores ------------------------------------
-    T *out = a.dst + (size_t)(y + 1) * a.pitch + x0;
-#pragma unroll
-    for (int q = 0; q < Q; ++q) store_vec(out + (size_t)q * a.plane, g[q]);
-
-    // ---- phase 5 (P2P face rows): the halo, written where the neighbour reads it --
-    if (P2P) {
-        const HaloP2P &p = a.halo;
-        if (y == a.H - 1 && p.down_dst) {            // dy=+1 movers -> lower neighbour's ghost row −1 (plane row 0)
-            T *peer = (T *)p.down_dst + x0;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) if (ey_of(q) == 1) store_vec(peer + (size_t)q * p.down_plane, g[q]);
-        }
-        if (y == 0 && p.up_dst) {                    // dy=−1 movers -> upper neighbour's ghost row H_up
-            T *peer = (T *)p.up_dst + (size_t)p.up_ghost_row * a.pitch + x0;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) if (ey_of(q) == -1) store_vec(peer + (size_t)q * p.up_plane, g[q]);
-        }
-    }
-}
-
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
-__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<T, COL>())
-step_vec_kernel(const __grid_constant__ StepArgs<T> a)
-{
-    // MULTIROW=false: one row per block (blockDim.y == 1), so the row index and all
-    // nine source-row addresses are block-uniform and live in uniform registers.
-    // let the next step's kernel start filling SM slots as soon as every block of this
-    // one has been scheduled (its blocks then wait in griddepcontrol.wait)
-    asm volatile("griddepcontrol.launch_dependents;");
-    // 1-D grid, x-chunk fastest: blocks that are scheduled together work on neighbouring
-    // chunks of the same rows, so the 18 streams advance through DRAM pages in order
-    // (measured +4 % over row-fastest block order).
-    const int rg = blockIdx.x / a.xchunks, xc = blockIdx.x - rg * a.xchunks;
-    const int yi = MULTIROW ? rg * blockDim.y + threadIdx.y : rg;
-    if (yi >= a.y_count) return;                     // warp-uniform
-    step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, a.y_begin + yi * a.y_stride,
-                                                       xc * blockDim.x + threadIdx.x, threadIdx.x & 31, 0);
-}
-
-// ---- fused face update + halo exchange over peer memory ------------------------
-// One launch updates the two face rows {0, H−1} of a slab and delivers the
-// populations that cross each face into the neighbouring GPUs' ghost rows with plain
-// stores through NVLink-mapped pointers (cudaIpc): compute and exchange are ONE kernel,
-// there is no pack buffer and no separate communication kernel.
-// Flow control is a step counter per face in each GPU's memory:
-//   wait   : ghost rows of step t are valid once the neighbour published flag >= t
-//   signal : after every block has stored (and fenced) its rows, the last block to
-//            finish publishes t+1 into both neighbours' flags
-// A-B buffering makes one step of slack enough: a neighbour that is one step ahead
-// writes into the buffer this GPU is not reading.
-__device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned want, int *error)
-{
-    if (!flag) return;
-    unsigned spins = 0;
-    while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - want) < 0) {
-        __nanosleep(128);
-        if (++spins > (1u << 27)) { atomicExch(error, 1); break; }   // ~20 s: report instead of hanging
-    }
-    __threadfence_system();
-}
-
-// One thread waits for both neighbours' step flags, the block follows through a barrier.
-// Returns 0 through shared memory: an order token for the ghost-row loads (see ldg_*).
-__device__ __forceinline__ int order_after_halo_flags(const HaloP2P &p)
-{
-    __shared__ int token;
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        wait_flag(p.wait_up, p.step, p.error);
-        wait_flag(p.wait_down, p.step, p.error);
-        token = 0;
-    }
-    __syncthreads();
-    return *reinterpret_cast<volatile int *>(&token);
-}
-
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
-__global__ void __launch_bounds__(STEP_THREADS, 1)
-step_face_p2p_kernel(const __grid_constant__ StepArgs<T> a)
-{
-    const HaloP2P &p = a.halo;
-    const int halo_tok = order_after_halo_flags(p);
-    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
-    if (yi < a.y_count)
-        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, a.y_begin + yi * a.y_stride,
-                                                          blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31,
-                                                          halo_tok);
-    __threadfence_system();                          // my stores (local and peer) are visible system-wide ...
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
-        if (atomicAdd(p.done, 1u) == total - 1) {    // ... before the last block publishes the step
-            *p.done = 0;
-            __threadfence_system();
-            if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
-            if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
-        }
-    }
-}
-
-// ---- the fused step, one cell per thread (any width) -------------------------
-template <typename T, int COL>
-__global__ void __launch_bounds__(STEP_THREADS)
-step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
-{
-    const int x = blockIdx.y * blockDim.x + threadIdx.x;
-    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
-    if (yi >= a.y_count || x >= a.W) return;
-    const int y = a.y_begin + yi * a.y_stride;
-    T c[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        int sy = y - ey_of(q);
-        if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
-        int sx = x - ex_of(q);
-        bool inside = true;
-        if (sx < 0)         { if (a.periodic_x) sx = a.W - 1; else inside = false; }
-        else if (sx >= a.W) { if (a.periodic_x) sx = 0;       else inside = false; }
-        c[q] = inside ? a.src[(size_t)q * a.plane + (size_t)(sy + 1) * a.pitch + sx] : T(0);
-    }
-    if (a.has_mask) bounce_back(c, a.mask[(size_t)y * a.mask_pitch + x] != 0);
-    collide<COL>(c, a.k);
-#pragma unroll
-    for (int q = 0; q < Q; ++q) a.dst[(size_t)q * a.plane + (size_t)(y + 1) * a.pitch + x] = c[q];
-}
 
 // ---- compute_equilibrium on the device (src/lbm.rs:43-71) --------------------
 template <typename T>
@@ -628,9 +286,6 @@ inline int reduction_blocks(size_t cells)
     return (int)b;
 }
 
-template <typename T>
-bool use_vec(const StepArgs<T> &a) { return a.W % VecOf<T>::N == 0; }
-
 }  // namespace
 
 template <typename T>
@@ -638,117 +293,6 @@ const char *step_kernel_name(const StepArgs<T> &a)
 {
     if (!use_vec(a)) return sizeof(T) == 4 ? "step_scalar_kernel<float>" : "step_scalar_kernel<double>";
     return sizeof(T) == 4 ? "step_vec_kernel<float>" : "step_vec_kernel<double>";
-}
-
-// Back-to-back step kernels are launched as programmatic dependents of each other
-// (CHEMSIM_LBM_PDL=0 in the environment restores plain stream order).
-inline bool pdl_enabled()
-{
-    static const bool on = [] { const char *e = getenv("CHEMSIM_LBM_PDL"); return !(e && e[0] == '0'); }();
-    return on;
-}
-
-template <typename T>
-void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cudaStream_t s, const StepArgs<T> &a)
-{
-    if (!pdl_enabled()) { kernel<<<grid, block, 0, s>>>(a); return; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, a);
-}
-
-template <typename T, int COL>
-void launch_step_col(const StepArgs<T> &a_in, cudaStream_t s)
-{
-    const int rows = a_in.y_count;
-    if (use_vec(a_in)) {
-        constexpr int V = VecOf<T>::N;
-        const int nvec = a_in.W / V;
-        int bx = ((nvec + 31) / 32) * 32;
-        if (bx > STEP_THREADS) bx = STEP_THREADS;
-        int by = STEP_THREADS / bx;
-        if (by > rows) by = rows;
-        const dim3 block(bx, by);
-        StepArgs<T> a = a_in;
-        a.xchunks = (nvec + bx - 1) / bx;
-        const dim3 grid((unsigned)a.xchunks * (unsigned)((rows + by - 1) / by));
-#define CHEMSIM_LAUNCH_VEC(PX, HM)                                                                   \
-        do {                                                                                         \
-            if (by == 1) launch_chained(step_vec_kernel<T, PX, HM, COL, false>, grid, block, s, a);  \
-            else         launch_chained(step_vec_kernel<T, PX, HM, COL, true>, grid, block, s, a);   \
-        } while (0)
-        if (a.periodic_x) {
-            if (a.has_mask) CHEMSIM_LAUNCH_VEC(true, true); else CHEMSIM_LAUNCH_VEC(true, false);
-        } else {
-            if (a.has_mask) CHEMSIM_LAUNCH_VEC(false, true); else CHEMSIM_LAUNCH_VEC(false, false);
-        }
-#undef CHEMSIM_LAUNCH_VEC
-    } else {
-        int bx = ((a_in.W + 31) / 32) * 32;
-        if (bx > STEP_THREADS) bx = STEP_THREADS;
-        int by = STEP_THREADS / bx;
-        if (by > rows) by = rows;
-        const dim3 block(bx, by);
-        const dim3 grid((rows + by - 1) / by, (a_in.W + bx - 1) / bx);
-        step_scalar_kernel<T, COL><<<grid, block, 0, s>>>(a_in);
-    }
-}
-
-// ---- the whole slab step + halo in ONE kernel (peer-memory mode) ------------------
-// 1-D grid of x-chunks x H blocks, x-chunk fastest; row slot r = 0 -> row 0, 1 -> row H−1,
-// r >= 2 -> row r−1, so the two face rows are dispatched first: they wait for the neighbours' step flags, update
-// their rows, store the outgoing populations into the neighbours' ghost rows and publish
-// the next step early, while the remaining blocks stream through the interior.  One
-// launch per step and GPU, chained with programmatic dependent launch; no events, no
-// communication kernel, no second stream.
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
-__global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<T, COL>())
-step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
-{
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int r = blockIdx.x / a.xchunks, xc = blockIdx.x - r * a.xchunks;
-    const int y = r == 0 ? 0 : (r == 1 ? a.H - 1 : r - 1);
-    const int xv = xc * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if (r >= 2) {                                    // interior row: reads no ghost row
-        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, y, xv, lane, 0);
-        return;
-    }
-    const HaloP2P &p = a.halo;
-    const int halo_tok = order_after_halo_flags(p);
-    step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane, halo_tok);
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned nface = (a.H > 1 ? 2u : 1u) * (unsigned)a.xchunks;
-        if (atomicAdd(p.done, 1u) == nface - 1) {
-            *p.done = 0;
-            __threadfence_system();
-            if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
-            if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
-        }
-    }
-}
-
-template <typename T, int COL>
-void launch_slab_p2p_col(const StepArgs<T> &a_in, cudaStream_t s)
-{
-    constexpr int V = VecOf<T>::N;
-    const int nvec = a_in.W / V;
-    const dim3 block(STEP_THREADS, 1);
-    StepArgs<T> a = a_in;
-    a.xchunks = (nvec + STEP_THREADS - 1) / STEP_THREADS;
-    const dim3 grid((unsigned)a.xchunks * (unsigned)a.H);
-    if (a.periodic_x) {
-        if (a.has_mask) launch_chained(step_slab_p2p_kernel<T, true, true, COL>, grid, block, s, a);
-        else            launch_chained(step_slab_p2p_kernel<T, true, false, COL>, grid, block, s, a);
-    } else {
-        if (a.has_mask) launch_chained(step_slab_p2p_kernel<T, false, true, COL>, grid, block, s, a);
-        else            launch_chained(step_slab_p2p_kernel<T, false, false, COL>, grid, block, s, a);
-    }
 }
 
 // one block per row chunk needs full 256-thread rows; narrower lattices use the
@@ -772,26 +316,6 @@ int launch_slab_p2p(const StepArgs<T> &a, cudaStream_t s)
     }
     const int e = check_launch();
     return e ? e : 1;
-}
-
-template <typename T, int COL>
-void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s)
-{
-    constexpr int V = VecOf<T>::N;
-    const int rows = a.y_count, nvec = a.W / V;
-    int bx = ((nvec + 31) / 32) * 32;
-    if (bx > STEP_THREADS) bx = STEP_THREADS;
-    int by = STEP_THREADS / bx;
-    if (by > rows) by = rows;
-    const dim3 block(bx, by);
-    const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
-    if (a.periodic_x) {
-        if (a.has_mask) step_face_p2p_kernel<T, true, true, COL><<<grid, block, 0, s>>>(a);
-        else            step_face_p2p_kernel<T, true, false, COL><<<grid, block, 0, s>>>(a);
-    } else {
-        if (a.has_mask) step_face_p2p_kernel<T, false, true, COL><<<grid, block, 0, s>>>(a);
-        else            step_face_p2p_kernel<T, false, false, COL><<<grid, block, 0, s>>>(a);
-    }
 }
 
 template <typename T>

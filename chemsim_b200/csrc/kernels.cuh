@@ -42,8 +42,22 @@ struct StepArgs {
     const uint8_t *mask_flags;  // per row, one byte per 64-cell segment: any solid cell in it?
     int flag_pitch;             // (a warp of the vector kernel covers whole segments and skips
                                 //  the mask load when they are solid-free)
+    // byte offsets from a thread's own-row pointer of population 0, precomputed by the host
+    // (fill_offsets): loads of population q come from row y - ey_q, stores go to row y
+    long long ld_off[Q];   // (q*plane - ey_q*pitch) * sizeof(T)
+    long long st_off[Q];   // q*plane * sizeof(T)
+    long long wrap_bytes;  // H*pitch*sizeof(T): what wrap_y adds/subtracts for the rows 0 / H-1
     HaloP2P halo;
     Consts<T> k;
+
+    void fill_offsets()
+    {
+        for (int q = 0; q < Q; ++q) {
+            st_off[q] = (long long)q * (long long)plane * (long long)sizeof(T);
+            ld_off[q] = st_off[q] - (long long)ey_of(q) * pitch * (long long)sizeof(T);
+        }
+        wrap_bytes = (long long)H * pitch * (long long)sizeof(T);
+    }
 };
 
 enum ReadoutKind : int {

@@ -1,0 +1,34 @@
+// step_decl.cuh — interface between the dispatch in kernels.cu and the per-operator
+// translation units (step_bgk.cu, step_trt.cu, step_regularized.cu, step_kbc.cu) that hold the
+// instantiations of the fused step kernels.  One TU per collision operator keeps the build
+// parallel (the step kernels are ~95 % of the library's compile time).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace chemsim {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float>  { using type = float4;  static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+
+// Build-time tunables (defaults are the measured best; tools/variants.py sweeps them).
+#ifndef CHEMSIM_STEP_THREADS
+#define CHEMSIM_STEP_THREADS 256
+#endif
+#ifndef CHEMSIM_STEP_MIN_BLOCKS
+#define CHEMSIM_STEP_MIN_BLOCKS 4   // <= 64 registers: 4 x 256 threads per SM (ptxas otherwise takes 88 for f64)
+#endif
+constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
+
+// widths that are a multiple of the vector width take the 128-bit kernels
+template <typename T>
+inline bool use_vec(const StepArgs<T> &a) { return a.W % VecOf<T>::N == 0; }
+
+// Defined (and explicitly instantiated for float/double) in step_<operator>.cu:
+// rows [y_begin, ...) of a lattice / the whole slab incl. the peer-memory halo / the two face rows.
+template <typename T, int COL> void launch_step_col(const StepArgs<T> &a, cudaStream_t s);
+template <typename T, int COL> void launch_slab_p2p_col(const StepArgs<T> &a, cudaStream_t s);
+template <typename T, int COL> void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s);
+
+}  // namespace chemsim
