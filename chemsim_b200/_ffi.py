@@ -80,7 +80,18 @@ PROTOTYPES = {
     "chemsim_lbm_cuda_stream": (_I, [_H, C.POINTER(_P)]),
     "chemsim_lbm_kernel_launches": (_I, [_H, C.POINTER(C.c_uint64)]),
     "chemsim_lbm_step_kernel_name": (C.c_char_p, [_H]),
+    "chemsim_lbm_barrier": (_I, [_H]),
+    "chemsim_lbm_set_p2p_timeout": (_I, [_H, _D]),
+    "chemsim_lbm_fill_geometry": (_I, [_H, _I]),
+    "chemsim_lbm_paint_rect": (_I, [_H, _I, _I, _I, _I, _I]),
+    "chemsim_lbm_get_async": (_I, [_H, _I, _I, _P, _P, _SZ]),
+    "chemsim_lbm_checkpoint_bytes": (_I, [_H, C.POINTER(_SZ)]),
+    "chemsim_lbm_checkpoint": (_I, [_H, _P, _SZ]),
+    "chemsim_lbm_restore": (_I, [_H, _P, _SZ]),
 }
+ABI_VERSION = 2
+(FIELD_DENSITY, FIELD_PRESSURE, FIELD_SPEED, FIELD_VELOCITY, FIELD_MOMENTUM_DENSITY, FIELD_POPULATION,
+ FIELD_EQUILIBRIUM, FIELD_NON_EQUILIBRIUM) = range(8)
 
 
 

@@ -159,6 +159,14 @@ mask_flags_kernel(const uint8_t *mask, int mask_pitch, int W, int row_begin, int
     if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) atomicOr(any, 1);
 }
 
+// Live geometry edit (src/main.rs:71-91 rewrites the mask on the host for every mouse event):
+// set the cells of a rectangle, one thread per cell.
+__global__ void paint_rect_kernel(uint8_t *mask, int mask_pitch, int x0, int y0, int w, int h, uint8_t value)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w && y < h) mask[(size_t)(y0 + y) * mask_pitch + x0 + x] = value;
+}
+
 // ---- device-side render.rs -----------------------------------------------------
 // The scalar a render mode normalises: render_scalar_field (src/render.rs:23-89) uses
 // the field itself, render_vector_field (:91-178) uses mag = vx*vx + vy*vy.
@@ -428,6 +436,14 @@ int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin,
     const int segs = (W + MASK_SEGMENT - 1) / MASK_SEGMENT;
     const int blocks = reduction_blocks((size_t)rows * segs);
     mask_flags_kernel<<<blocks, RED_THREADS, 0, s>>>(mask, mask_pitch, W, row_begin, rows, flags, flag_pitch, any);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+int launch_paint_rect(uint8_t *mask, int mask_pitch, int x0, int y0, int w, int h, uint8_t value, cudaStream_t s)
+{
+    const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    paint_rect_kernel<<<grid, block, 0, s>>>(mask, mask_pitch, x0, y0, w, h, value);
     const int e = check_launch();
     return e ? e : 1;
 }

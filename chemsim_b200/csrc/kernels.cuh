@@ -20,7 +20,9 @@ struct HaloP2P {
     unsigned *signal_up = nullptr, *signal_down = nullptr;     // the neighbours' flags this GPU publishes into
     unsigned *done = nullptr;                      // local counter of finished blocks
     unsigned step = 0;                             // t: needs flags >= t, publishes t+1
-    int *error = nullptr;                          // set to 1 if a wait timed out
+    int *error = nullptr;                          // device word: set to 1 if a wait timed out (sticky until re-upload)
+    int *error_host = nullptr;                     // the same in mapped host memory, for the host API
+    unsigned long long timeout_ns = 0;             // how long a face block waits for a neighbour's flag
 };
 
 template <typename T>
@@ -115,5 +117,8 @@ constexpr int MASK_SEGMENT = 64;   // cells per mask-flag byte
 // recompute the segment flags of rows [row_begin, row_begin + rows); *any |= 1 if a solid cell exists there
 int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin, int rows, uint8_t *flags,
                       int flag_pitch, int *any, cudaStream_t s);
+
+// set mask cells [y0, y0+h) x [x0, x0+w) (already clipped to the slab) to `value`
+int launch_paint_rect(uint8_t *mask, int mask_pitch, int x0, int y0, int w, int h, uint8_t value, cudaStream_t s);
 
 }  // namespace chemsim

@@ -13,6 +13,7 @@
 #include <ctime>
 #include <unistd.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -50,7 +51,8 @@ struct chemsim_lbm {
     int flag_pitch = 0;
     void *stage[3] = {nullptr, nullptr, nullptr};   // dense staging fields (grown on demand)
     size_t stage_bytes[3] = {0, 0, 0};
-    void *snap[2] = {nullptr, nullptr};             // full-field snapshots for asynchronous readouts
+    void *snap[2] = {nullptr, nullptr};             // field snapshots (up to two planes each) for asynchronous readouts
+    size_t snap_bytes[2] = {0, 0};
     int snap_next = 0;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_main = nullptr, ev_mask = nullptr, ev_snap_ready[2] = {nullptr, nullptr},
@@ -68,7 +70,11 @@ struct chemsim_lbm {
     // neighbours' ghost rows directly; NCCL is then only used for the first exchange
     int halo_mode = CHEMSIM_LBM_HALO_NCCL;
     unsigned step_index = 0;                        // steps taken since creation (same on every rank)
-    unsigned *p2p_flags = nullptr;                  // [0] from_up, [1] from_down, [2] done counter, [3] error
+    unsigned *p2p_flags = nullptr;                  // [0] from_up, [1] from_down, [2] done counter, [3] error (device copy)
+    int *p2p_error_host = nullptr;                  // mapped host word the kernels set on a halo time-out
+    int *p2p_error_dev = nullptr;                   // its device-side address
+    double p2p_timeout_s = 30.0;                    // CHEMSIM_LBM_P2P_TIMEOUT_S / chemsim_lbm_set_p2p_timeout
+    int stream_mirrored = 0;                        // chemsim_lbm_set_stream_convention
     void *peer_up_buf[2] = {nullptr, nullptr}, *peer_down_buf[2] = {nullptr, nullptr};
     unsigned *peer_up_flags = nullptr, *peer_down_flags = nullptr;
     int peer_up_H = 0, peer_down_H = 0;
@@ -231,8 +237,22 @@ void fill_halo(const chemsim_lbm *h, HaloP2P &p)
     }
     p.done = h->p2p_flags + 2;
     p.error = (int *)(h->p2p_flags + 3);
+    p.error_host = h->p2p_error_dev;
+    p.timeout_ns = (unsigned long long)(h->p2p_timeout_s * 1e9);
     p.step = h->step_index;
 }
+
+// A halo time-out is sticky (until the next upload): every call that produces or consumes
+// lattice data reports it instead of returning numbers computed from a stale halo.
+int check_p2p_error(chemsim_lbm *h)
+{
+    if (h->p2p_error_host && *(volatile int *)h->p2p_error_host)
+        return fail(h, CHEMSIM_LBM_ERR_CUDA,
+                    "peer-memory halo: a neighbour did not publish its face rows within the time-out; the lattice "
+                    "holds a stale halo (upload new populations on every rank to recover)");
+    return 0;
+}
+#define P2P_CHECK(h) do { const int e_ = check_p2p_error(h); if (e_) return e_; } while (0)
 
 struct P2PInfo {                 // what the ranks tell each other (all-gathered over NCCL)
     cudaIpcMemHandle_t buf[2];
@@ -255,7 +275,11 @@ bool map_peer(chemsim_lbm *h, const P2PInfo &peer, void *(&buf)[2], unsigned *&f
 {
     if (peer.pid == (long long)getpid()) {          // same process: direct peer pointers
         via_ipc = false;
-        if (peer.device != h->device) {
+        // Two slabs on ONE device cannot use the flag handshake: with programmatic dependent launch the
+        // next step's blocks of one slab may occupy the SM slots the other slab's face blocks need
+        // while they spin on that slab's flag.  Such lattices keep the NCCL exchange.
+        if (peer.device == h->device) return false;
+        {
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, h->device, peer.device) != cudaSuccess || !can) return false;
             const cudaError_t e = cudaDeviceEnablePeerAccess(peer.device, 0);
@@ -305,6 +329,19 @@ int enable_p2p(chemsim_lbm *h)
     if (!h->p2p_flags) {
         if (cudaMalloc((void **)&h->p2p_flags, 4 * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
         else if (cudaMemset(h->p2p_flags, 0, 4 * sizeof(unsigned)) != cudaSuccess) mine.ok = 0;
+    }
+    if (!h->p2p_error_host) {
+        if (cudaHostAlloc((void **)&h->p2p_error_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void **)&h->p2p_error_dev, h->p2p_error_host, 0) != cudaSuccess) {
+            mine.ok = 0;
+            cudaGetLastError();
+        } else {
+            *h->p2p_error_host = 0;
+        }
+        if (const char *e = getenv("CHEMSIM_LBM_P2P_TIMEOUT_S")) {
+            const double t = atof(e);
+            if (t > 0.0) h->p2p_timeout_s = t;
+        }
     }
     const bool vec_ok = h->dtype == CHEMSIM_LBM_F32 ? face_p2p_supported(step_args<float>(h, 0, 1))
                                                     : face_p2p_supported(step_args<double>(h, 0, 1));
@@ -388,6 +425,15 @@ int begin_sharded(chemsim_lbm *h)
     CUDA_TRY(h, cudaEventRecord(h->ev_interior, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_interior, 0));
     if (!h->ghosts_valid) {
+        if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
+            // New populations (upload / restore) on every rank: restart the flag handshake from the
+            // current step and clear a previous time-out.  My own kernels have finished (uploads
+            // synchronise the stream); a neighbour cannot publish a NEWER step into these flags
+            // before it has passed the NCCL exchange below, which needs this rank to get there too.
+            const unsigned init[4] = {h->step_index, h->step_index, 0u, 0u};
+            CUDA_TRY(h, cudaMemcpy(h->p2p_flags, init, sizeof(init), cudaMemcpyHostToDevice));
+            *(volatile int *)h->p2p_error_host = 0;
+        }
         const int r = exchange(h, h->cur);
         if (r) return r;
         h->ghosts_valid = true;
@@ -486,24 +532,45 @@ int readout_impl(chemsim_lbm *h, int kind, int q, void *dst0, void *dst1)
     CUDA_TRY(h, cudaMemcpyAsync(dst0, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
     if (dst1) CUDA_TRY(h, cudaMemcpyAsync(dst1, h->stage[1], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
     return 0;
 }
 
-// Asynchronous density snapshot: the readout kernel runs on the main stream into
-// one of two snapshot buffers, the device->host copy on its own stream, so the
-// next steps overlap with the transfer (record/render "on demand").
+// Asynchronous field snapshot (record/render "on demand"): the readout kernel runs
+// on the main stream into one of two snapshot buffers, the device->host copy on its own stream,
+// so the next steps overlap with the transfer.  A population is snapshotted with a strided
+// device copy (the lattice buffer itself is overwritten two steps later).
 template <typename T>
-int density_async_impl(chemsim_lbm *h, void *dst)
+int snapshot_async_impl(chemsim_lbm *h, int field, int q, void *dst0, void *dst1)
 {
     const size_t bytes = (size_t)h->W * h->H * sizeof(T);
+    const bool two = dst1 != nullptr;
     const int slot = h->snap_next;
     h->snap_next ^= 1;
-    if (!h->snap[slot]) CUDA_TRY(h, cudaMalloc(&h->snap[slot], bytes));
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_snap_done[slot], 0));   // previous copy out of this slot
-    LAUNCH_TRY(h, launch_readout<T>(readout_args<T>(h, READ_DENSITY, 0, h->snap[slot], nullptr), h->stream));
+    if (h->snap_bytes[slot] < (two ? 2 : 1) * bytes) {
+        if (h->snap[slot]) {
+            CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            CUDA_TRY(h, cudaFree(h->snap[slot]));
+            h->snap[slot] = nullptr; h->snap_bytes[slot] = 0;
+        }
+        CUDA_TRY(h, cudaMalloc(&h->snap[slot], 2 * bytes));
+        h->snap_bytes[slot] = 2 * bytes;
+    }
+    char *s0 = (char *)h->snap[slot], *s1 = s0 + bytes;
+    if (field == CHEMSIM_LBM_FIELD_POPULATION) {
+        CUDA_TRY(h, cudaMemcpy2DAsync(s0, (size_t)h->W * sizeof(T), row_ptr(h, h->cur, q, 0), (size_t)h->pitch * sizeof(T),
+                                      (size_t)h->W * sizeof(T), h->H, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        static const int kind_of[] = {READ_DENSITY, READ_PRESSURE, READ_SPEED, READ_VELOCITY, READ_MOMENTUM, -1,
+                                      READ_EQUILIBRIUM, READ_NON_EQUILIBRIUM};
+        LAUNCH_TRY(h, launch_readout<T>(readout_args<T>(h, kind_of[field], q, s0, two ? s1 : nullptr), h->stream));
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev_snap_ready[slot], h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_snap_ready[slot], 0));
-    CUDA_TRY(h, cudaMemcpyAsync(dst, h->snap[slot], bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dst0, s0, bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (two) CUDA_TRY(h, cudaMemcpyAsync(dst1, s1, bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
     CUDA_TRY(h, cudaEventRecord(h->ev_snap_done[slot], h->d2h_stream));
     return 0;
 }
@@ -644,7 +711,7 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
         CREATE_TRY(cudaEventCreateWithFlags(&h->ev_snap_done[i], cudaEventDisableTiming));
     }
     CREATE_TRY(cudaMalloc((void **)&h->d_partials, sizeof(double) * mass_partials_capacity()));
-    CREATE_TRY(cudaMalloc((void **)&h->d_scalar, 4 * sizeof(double)));
+    CREATE_TRY(cudaMalloc((void **)&h->d_scalar, 8 * sizeof(double)));   // [0..3] reductions, [4..5] barrier scratch
     CREATE_TRY(cudaMalloc((void **)&h->d_flag, sizeof(int)));
     CREATE_TRY(cudaMallocHost((void **)&h->h_scalar, 2 * sizeof(double)));
     CREATE_TRY(cudaMallocHost((void **)&h->h_flag, sizeof(int)));
@@ -751,18 +818,30 @@ int chemsim_lbm_destroy(chemsim_lbm_t *h)
         // the last step, i.e. their last face kernel has finished.
         const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
         const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
-        for (int spin = 0; spin < 5000; ++spin) {
+        bool quiesced = false;
+        const int max_spins = (int)(h->p2p_timeout_s * 1000.0) + 1;
+        for (int spin = 0; spin < max_spins; ++spin) {
             unsigned f[2] = {0, 0};
             if (cudaMemcpy(f, h->p2p_flags, sizeof(f), cudaMemcpyDeviceToHost) != cudaSuccess) break;
             const bool up_done = !has_up || (int)(f[0] - h->step_index) >= 0;
             const bool down_done = !has_down || (int)(f[1] - h->step_index) >= 0;
-            if (up_done && down_done) break;
+            if (up_done && down_done) { quiesced = true; break; }
             struct timespec ts = {0, 1000000};
             nanosleep(&ts, nullptr);
         }
         close_p2p(h);
+        if (!quiesced) {
+            // A neighbour has not published the last step: its face kernel may still store into my
+            // ghost rows and flags through its peer mapping.  Leak those allocations rather than
+            // hand the neighbour a dangling pointer (device-side use-after-free).
+            fprintf(stderr, "chemsim_lbm_destroy: rank %d: a neighbour has not finished step %u; "
+                            "population buffers and halo flags are not freed\n", h->rank, h->step_index);
+            h->buf[0] = h->buf[1] = nullptr;
+            h->p2p_flags = nullptr;
+        }
     }
     if (h->p2p_flags) cudaFree(h->p2p_flags);
+    if (h->p2p_error_host) cudaFreeHost(h->p2p_error_host);
     if (h->comm) nccl_dyn().CommDestroy(h->comm);
     for (int b = 0; b < 2; ++b) if (h->buf[b]) cudaFree(h->buf[b]);
     if (h->h2d_stream) cudaStreamSynchronize(h->h2d_stream);
@@ -883,6 +962,7 @@ int chemsim_lbm_kinematic_shear_viscosity(const chemsim_lbm_t *h, double *out)
 
 int chemsim_lbm_kinematic_bulk_viscosity(const chemsim_lbm_t *h, double *out)
 {
+    if (!h || !out) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
     double nu = 0.0;
     const int r = chemsim_lbm_kinematic_shear_viscosity(h, &nu);
     if (r) return r;
@@ -981,6 +1061,55 @@ int chemsim_lbm_set_geometry_async(chemsim_lbm_t *h, const uint8_t *solid, size_
     return CHEMSIM_LBM_OK;
 }
 
+int chemsim_lbm_fill_geometry(chemsim_lbm_t *h, int value)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    BIND(h);
+    const uint8_t v = value ? 1 : 0;
+    CUDA_TRY(h, cudaMemset2DAsync(h->mask, h->mask_pitch, v, h->W, h->H, h->stream));
+    const int segs = (h->W + MASK_SEGMENT - 1) / MASK_SEGMENT;
+    CUDA_TRY(h, cudaMemset2DAsync(h->mask_flags, h->flag_pitch, v, segs, h->H, h->stream));
+    h->has_mask = v;                    // all-fluid: the mask-free kernel; all-solid: consult the flags
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_paint_rect(chemsim_lbm_t *h, int x0, int y0, int width, int height, int value)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (width < 0 || height < 0) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "negative rectangle size");
+    BIND(h);
+    // clip to the lattice in x and to this handle's slab in y (y is a GLOBAL row)
+    long long xa = x0, xb = (long long)x0 + width, ya = (long long)y0 - h->row0, yb = ya + height;
+    if (xa < 0) xa = 0;
+    if (xb > h->W) xb = h->W;
+    if (ya < 0) ya = 0;
+    if (yb > h->H) yb = h->H;
+    if (xa >= xb || ya >= yb) return CHEMSIM_LBM_OK;          // nothing of it on this slab
+    LAUNCH_TRY(h, launch_paint_rect(h->mask, h->mask_pitch, (int)xa, (int)ya, (int)(xb - xa), (int)(yb - ya),
+                                    value ? 1 : 0, h->stream));
+    LAUNCH_TRY(h, launch_mask_flags(h->mask, h->mask_pitch, h->W, (int)ya, (int)(yb - ya), h->mask_flags, h->flag_pitch,
+                                    h->d_flag, h->stream));
+    if (value) h->has_mask = 1;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_barrier(chemsim_lbm_t *h)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (h->nranks == 1) return CHEMSIM_LBM_OK;
+    BIND(h);
+    NCCL_TRY(h, nccl_dyn().AllReduce(h->d_scalar + 4, h->d_scalar + 5, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    h->launches += 1;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_p2p_timeout(chemsim_lbm_t *h, double seconds)
+{
+    if (!h || !(seconds > 0.0)) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    h->p2p_timeout_s = seconds;
+    return CHEMSIM_LBM_OK;
+}
+
 int chemsim_lbm_step(chemsim_lbm_t *h, int nsteps)
 {
     if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
@@ -988,6 +1117,7 @@ int chemsim_lbm_step(chemsim_lbm_t *h, int nsteps)
     if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set (init_equilibrium / set_population)");
     if (h->col.kind == COL_NONE) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "collision operator not set (set_bgk / set_trt / set_regularized / set_kbc)");
     BIND(h);
+    P2P_CHECK(h);
     const int r = h->dtype == CHEMSIM_LBM_F32 ? step_impl<float>(h, nsteps) : step_impl<double>(h, nsteps);
     if (r) return r;
     for (int s = 0; s < nsteps; ++s) {   // self.time += delta_t, in Scalar (src/lbm.rs:713)
@@ -1005,11 +1135,7 @@ int chemsim_lbm_synchronize(chemsim_lbm_t *h)
     CUDA_TRY(h, cudaStreamSynchronize(h->comm_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->h2d_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
-    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
-        int err = 0;
-        CUDA_TRY(h, cudaMemcpy(&err, h->p2p_flags + 3, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) return fail(h, CHEMSIM_LBM_ERR_CUDA, "peer-memory halo: a neighbour did not publish its face rows in time");
-    }
+    P2P_CHECK(h);
     return CHEMSIM_LBM_OK;
 }
 
@@ -1021,14 +1147,28 @@ int chemsim_lbm_time(const chemsim_lbm_t *h, double *out)
 }
 
 int chemsim_lbm_get_density(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_DENSITY, 0, dst, nullptr, n); }
-int chemsim_lbm_get_density_async(chemsim_lbm_t *h, void *dst, size_t n)
+int chemsim_lbm_get_async(chemsim_lbm_t *h, int field, int q, void *dst0, void *dst1, size_t n)
 {
-    if (!h || !dst) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h || !dst0) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (field < CHEMSIM_LBM_FIELD_DENSITY || field > CHEMSIM_LBM_FIELD_NON_EQUILIBRIUM)
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "unknown field");
+    const bool two = field == CHEMSIM_LBM_FIELD_VELOCITY || field == CHEMSIM_LBM_FIELD_MOMENTUM_DENSITY;
+    if (two != (dst1 != nullptr))
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "dst1 is for (and required by) the two-component fields");
+    const bool per_q = field >= CHEMSIM_LBM_FIELD_POPULATION;
+    if (per_q && (q < 0 || q >= Q)) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "q must be in 0..9");
     BIND(h);
     const int c = check_n(h, n);
     if (c) return c;
     if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
-    return h->dtype == CHEMSIM_LBM_F32 ? density_async_impl<float>(h, dst) : density_async_impl<double>(h, dst);
+    P2P_CHECK(h);
+    return h->dtype == CHEMSIM_LBM_F32 ? snapshot_async_impl<float>(h, field, q, dst0, dst1)
+                                       : snapshot_async_impl<double>(h, field, q, dst0, dst1);
+}
+
+int chemsim_lbm_get_density_async(chemsim_lbm_t *h, void *dst, size_t n)
+{
+    return chemsim_lbm_get_async(h, CHEMSIM_LBM_FIELD_DENSITY, 0, dst, nullptr, n);
 }
 
 int chemsim_lbm_get_pressure(chemsim_lbm_t *h, void *dst, size_t n) { return readout(h, READ_PRESSURE, 0, dst, nullptr, n); }
@@ -1057,6 +1197,7 @@ int chemsim_lbm_get_population(chemsim_lbm_t *h, int q, void *dst, size_t n)
     CUDA_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->W * h->esize, row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize,
                                   (size_t)h->W * h->esize, h->H, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
     return CHEMSIM_LBM_OK;
 }
 
@@ -1092,6 +1233,7 @@ int chemsim_lbm_total_mass(chemsim_lbm_t *h, double *out)
     if (r) return r;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_scalar, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
     *out = h->h_scalar[0];
     return CHEMSIM_LBM_OK;
 }
@@ -1108,6 +1250,7 @@ int chemsim_lbm_total_mass_global(chemsim_lbm_t *h, double *out)
     h->launches += 1;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_scalar, h->d_scalar + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
     *out = h->h_scalar[0];
     return CHEMSIM_LBM_OK;
 }
@@ -1147,6 +1290,7 @@ int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t
                                                   stats, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(rgba, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
     return CHEMSIM_LBM_OK;
 }
 
@@ -1164,7 +1308,87 @@ int chemsim_lbm_is_unstable(chemsim_lbm_t *h, int *out)
                                                  h->d_flag, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
     *out = *h->h_flag ? 1 : 0;
+    return CHEMSIM_LBM_OK;
+}
+
+// ---- checkpoint / restore -------------------------------------------------
+// Layout: chemsim_lbm_checkpoint_header, then the nine populations of this handle's slab as dense
+// row-major W x H planes in the lattice dtype, then the geometry (W x H bytes).
+static size_t checkpoint_size(const chemsim_lbm *h)
+{
+    const size_t cells = (size_t)h->W * h->H;
+    return sizeof(chemsim_lbm_checkpoint_header) + (size_t)Q * cells * h->esize + cells;
+}
+
+int chemsim_lbm_checkpoint_bytes(const chemsim_lbm_t *h, size_t *out)
+{
+    if (!h || !out) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *out = checkpoint_size(h);
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_checkpoint(chemsim_lbm_t *h, void *dst, size_t bytes)
+{
+    if (!h || !dst) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (bytes < checkpoint_size(h)) return fail(h, CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE, "checkpoint buffer too small");
+    if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    BIND(h);
+    chemsim_lbm_checkpoint_header hd;
+    std::memset(&hd, 0, sizeof(hd));
+    std::memcpy(hd.magic, CHEMSIM_LBM_CHECKPOINT_MAGIC, 8);
+    hd.header_bytes = (uint32_t)sizeof(hd);
+    hd.dtype = (uint32_t)h->dtype; hd.width = (uint32_t)h->W; hd.local_height = (uint32_t)h->H;
+    hd.global_height = (uint32_t)h->Hglobal; hd.row_offset = (uint32_t)h->row0;
+    hd.rank = (uint32_t)h->rank; hd.nranks = (uint32_t)h->nranks; hd.edge = (uint32_t)h->edge;
+    hd.collision = (uint32_t)h->col.kind; hd.step_index = h->step_index;
+    hd.time_f32 = h->time_f; hd.time_f64 = h->time_d;
+    hd.delta_x = h->dx; hd.delta_t = h->dt;
+    hd.tau = h->col.tau; hd.tau_plus = h->col.tau_plus; hd.tau_minus = h->col.tau_minus; hd.viscosity = h->col.viscosity;
+    char *out = (char *)dst;
+    std::memcpy(out, &hd, sizeof(hd));
+    out += sizeof(hd);
+    const size_t row = (size_t)h->W * h->esize, plane_bytes = row * h->H;
+    for (int q = 0; q < Q; ++q)
+        CUDA_TRY(h, cudaMemcpy2DAsync(out + (size_t)q * plane_bytes, row, row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize,
+                                      row, h->H, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(out + (size_t)Q * plane_bytes, h->W, h->mask, h->mask_pitch, h->W, h->H,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    P2P_CHECK(h);
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_restore(chemsim_lbm_t *h, const void *src, size_t bytes)
+{
+    if (!h || !src) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "null argument");
+    if (bytes < sizeof(chemsim_lbm_checkpoint_header)) return fail(h, CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE, "checkpoint truncated");
+    chemsim_lbm_checkpoint_header hd;
+    std::memcpy(&hd, src, sizeof(hd));
+    if (std::memcmp(hd.magic, CHEMSIM_LBM_CHECKPOINT_MAGIC, 8) != 0 || hd.header_bytes != sizeof(hd))
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "not a chemsim_lbm checkpoint (magic / header size)");
+    if ((int)hd.dtype != h->dtype || (int)hd.width != h->W || (int)hd.local_height != h->H ||
+        (int)hd.global_height != h->Hglobal || (int)hd.row_offset != h->row0)
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "checkpoint is of a different lattice (dtype / shape / slab)");
+    if (bytes < checkpoint_size(h)) return fail(h, CHEMSIM_LBM_ERR_INVALID_SLICE_SIZE, "checkpoint truncated");
+    BIND(h);
+    const char *in = (const char *)src + sizeof(hd);
+    const size_t row = (size_t)h->W * h->esize, plane_bytes = row * h->H;
+    for (int q = 0; q < Q; ++q)
+        CUDA_TRY(h, cudaMemcpy2DAsync(row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize, in + (size_t)q * plane_bytes, row,
+                                      row, h->H, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+    const int r = upload_geometry_rows(h, 0, h->H, (const uint8_t *)in + (size_t)Q * plane_bytes, h->stream);
+    if (r) return r;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->has_mask = *h->h_flag ? 1 : 0;
+    h->have_populations = true;
+    h->ghosts_valid = false;            // sharded: the next step exchanges the halo (collective, like any upload)
+    h->step_index = hd.step_index;
+    h->time_f = hd.time_f32;
+    h->time_d = hd.time_f64;
     return CHEMSIM_LBM_OK;
 }
 

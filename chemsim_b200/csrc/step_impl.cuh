@@ -274,15 +274,36 @@ step_vec_kernel(const __grid_constant__ StepArgs<T> a)
 //            finish publishes t+1 into both neighbours' flags
 // A-B buffering makes one step of slack enough: a neighbour that is one step ahead
 // writes into the buffer this GPU is not reading.
-__device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned want, int *error)
+__device__ __forceinline__ unsigned long long global_timer_ns()
 {
-    if (!flag) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin (with back-off) until the neighbour has published step `want`.  A neighbour that does
+// not show up within p.timeout_ns (host-side skew longer than that, a dead peer) is reported
+// through the error words — one in device memory for the kernels, one in mapped host memory
+// that every later API call checks — and the caller must then NOT publish its own step: the
+// stale halo stays on this GPU.
+__device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned want, const HaloP2P &p)
+{
+    if (!flag) return true;
+    const volatile unsigned *f = reinterpret_cast<const volatile unsigned *>(flag);
+    if ((int)(*f - want) >= 0) { __threadfence_system(); return true; }
+    const unsigned long long t0 = global_timer_ns();
     unsigned spins = 0;
-    while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - want) < 0) {
-        __nanosleep(128);
-        if (++spins > (1u << 27)) { atomicExch(error, 1); break; }   // ~20 s: report instead of hanging
+    while ((int)(*f - want) < 0) {
+        __nanosleep(spins < 64 ? 32 : 256);
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > p.timeout_ns) {
+            *reinterpret_cast<volatile int *>(p.error) = 1;          // device copy: checked by publish_step
+            *reinterpret_cast<volatile int *>(p.error_host) = 1;     // host copy: checked by the API calls
+            __threadfence_system();
+            return false;
+        }
     }
     __threadfence_system();
+    return true;
 }
 
 // One thread waits for both neighbours' step flags, the block follows through a barrier.
@@ -291,12 +312,26 @@ __device__ __forceinline__ int order_after_halo_flags(const HaloP2P &p)
 {
     __shared__ int token;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        wait_flag(p.wait_up, p.step, p.error);
-        wait_flag(p.wait_down, p.step, p.error);
+        wait_flag(p.wait_up, p.step, p);
+        wait_flag(p.wait_down, p.step, p);
         token = 0;
     }
     __syncthreads();
     return *reinterpret_cast<volatile int *>(&token);
+}
+
+// The last face block to finish publishes step t+1 into both neighbours' flags — unless a wait
+// timed out (now or in an earlier step): a poisoned lattice never tells its neighbours to go on,
+// so they time out as well instead of consuming a stale halo.
+__device__ __forceinline__ void publish_step(const HaloP2P &p, unsigned total_face_blocks)
+{
+    if (atomicAdd(p.done, 1u) == total_face_blocks - 1) {
+        *p.done = 0;
+        __threadfence_system();
+        if (*reinterpret_cast<volatile int *>(p.error) != 0) return;
+        if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
+        if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
+    }
 }
 
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
@@ -312,15 +347,8 @@ step_face_p2p_kernel(const __grid_constant__ StepArgs<T> a)
                                                           halo_tok);
     __threadfence_system();                          // my stores (local and peer) are visible system-wide ...
     __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
-        if (atomicAdd(p.done, 1u) == total - 1) {    // ... before the last block publishes the step
-            *p.done = 0;
-            __threadfence_system();
-            if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
-            if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
-        }
-    }
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+        publish_step(p, gridDim.x * gridDim.y);      // ... before the last block publishes the step
 }
 
 // ---- the fused step, one cell per thread (any width) -------------------------
@@ -443,15 +471,7 @@ step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane, halo_tok);
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned nface = (a.H > 1 ? 2u : 1u) * (unsigned)a.xchunks;
-        if (atomicAdd(p.done, 1u) == nface - 1) {
-            *p.done = 0;
-            __threadfence_system();
-            if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
-            if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
-        }
-    }
+    if (threadIdx.x == 0) publish_step(p, (a.H > 1 ? 2u : 1u) * (unsigned)a.xchunks);
 }
 
 }  // namespace

@@ -102,7 +102,7 @@ class BGK:
         t = np.dtype(dtype).type
         return t(2.0) * self.kinematic_shear_viscosity(disc, dtype) / t(3.0)
 
-    def _apply(self, handle):
+    def _apply(self, handle, disc=None, dtype=None):
         _ffi.check(_ffi.load().chemsim_lbm_set_bgk(handle, float(self.tau)), handle)
 
 
@@ -132,7 +132,7 @@ class TRT:
         cs = disc.isothermal_speed_of_sound(dtype)
         return cs * cs * (t(self.tau_plus) / t(disc.delta_t) - t(0.5))
 
-    def _apply(self, handle):
+    def _apply(self, handle, disc=None, dtype=None):
         _ffi.check(_ffi.load().chemsim_lbm_set_trt(handle, float(self.tau_plus), float(self.tau_minus)), handle)
 
 
@@ -148,7 +148,7 @@ class KBC:
     def kinematic_shear_viscosity(self, disc: Discretization, dtype=Scalar):
         return np.dtype(dtype).type(self.ks_viscosity)
 
-    def _apply(self, handle):
+    def _apply(self, handle, disc=None, dtype=None):
         _ffi.check(_ffi.load().chemsim_lbm_set_kbc(handle, float(self.ks_viscosity)), handle)
 
 
@@ -164,8 +164,10 @@ class Regularized:
     def kinematic_shear_viscosity(self, disc: Discretization, dtype=Scalar):
         return self.underlying.kinematic_shear_viscosity(disc, dtype)
 
-    def _apply(self, handle):
-        nu = float(self.underlying.kinematic_shear_viscosity(Discretization(), Scalar))
+    def _apply(self, handle, disc: Discretization = Discretization(), dtype=Scalar):
+        # Regularized::kinematic_shear_viscosity(disc) = underlying.kinematic_shear_viscosity(disc)
+        # (src/lbm.rs:663-665), with the State's discretization and dtype
+        nu = float(self.underlying.kinematic_shear_viscosity(disc, dtype))
         _ffi.check(_ffi.load().chemsim_lbm_set_regularized(handle, nu), handle)
 
 
@@ -253,10 +255,14 @@ class State:
         else:
             st = lib.chemsim_lbm_create(w, h, _dtype_code(dtype), edge, device, C.byref(handle))
         _ffi.check(st, None)
-        self = cls(handle, dtype, collision, discretization)
-        self._check(lib.chemsim_lbm_set_discretization(handle, float(discretization.delta_x),
-                                                       float(discretization.delta_t)))
-        collision._apply(handle)
+        try:
+            self = cls(handle, dtype, collision, discretization)
+            self._check(lib.chemsim_lbm_set_discretization(handle, float(discretization.delta_x),
+                                                           float(discretization.delta_t)))
+            collision._apply(handle, discretization, dtype)
+        except BaseException:
+            lib.chemsim_lbm_destroy(handle)      # do not leak the device-resident State
+            raise
         return self
 
     @classmethod
@@ -343,6 +349,47 @@ class State:
     def density_async(self, pinned_dst_ptr: int, n: int):
         """Asynchronous State::density into page-locked memory; valid after synchronize()."""
         self._check(self._lib.chemsim_lbm_get_density_async(self._h, C.c_void_p(pinned_dst_ptr), n))
+
+    def get_async(self, field: int, pinned_dst0: int, n: int, pinned_dst1: int | None = None, q: int = 0):
+        """Asynchronous form of any readout (field = _ffi.FIELD_*) into page-locked memory
+        (pointers + element count); valid after synchronize().  Two snapshots may be in flight."""
+        self._check(self._lib.chemsim_lbm_get_async(self._h, field, q, C.c_void_p(pinned_dst0),
+                                                    C.c_void_p(pinned_dst1) if pinned_dst1 else None, n))
+
+    def fill_geometry(self, value: bool):
+        """state.geometry = all `value`, on the device."""
+        self._check(self._lib.chemsim_lbm_fill_geometry(self._h, int(bool(value))))
+
+    def paint_rect(self, x0: int, y0: int, width: int, height: int, value: bool = True):
+        """Set geometry cells [x0, x0+width) x [y0, y0+height) (global rows) on the device."""
+        self._check(self._lib.chemsim_lbm_paint_rect(self._h, x0, y0, width, height, int(bool(value))))
+
+    def paint_brush(self, pos):
+        """The reference's mouse handler (src/main.rs:71-91) without its host round trip: the geometry
+        becomes exactly the 9x9 block around the cursor, row = floor(pos[1]), column = floor(pos[0])."""
+        row, col = int(np.floor(pos[1])), int(np.floor(pos[0]))
+        if 0 <= row < self.global_height and 0 <= col < self.width:        # main.rs:76
+            self.fill_geometry(False)
+            self.paint_rect(col - 4, row - 4, 9, 9, True)
+
+    def barrier(self):
+        """Device-side barrier over the ranks of a sharded lattice (asynchronous, collective)."""
+        self._check(self._lib.chemsim_lbm_barrier(self._h))
+
+    def set_p2p_timeout(self, seconds: float):
+        self._check(self._lib.chemsim_lbm_set_p2p_timeout(self._h, float(seconds)))
+
+    def checkpoint(self) -> np.ndarray:
+        """This handle's slab (populations, geometry, time, step counter) as bytes."""
+        n = C.c_size_t()
+        self._check(self._lib.chemsim_lbm_checkpoint_bytes(self._h, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        self._check(self._lib.chemsim_lbm_checkpoint(self._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+        return buf
+
+    def restore(self, blob):
+        blob = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob)
+        self._check(self._lib.chemsim_lbm_restore(self._h, blob.ctypes.data_as(C.c_void_p), blob.size))
 
     # ---- the hot path -----------------------------------------------------------
     def step(self, nsteps: int = 1):

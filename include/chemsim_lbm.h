@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CHEMSIM_LBM_ABI_VERSION 1
+#define CHEMSIM_LBM_ABI_VERSION 2
 #define CHEMSIM_LBM_Q 9
 #define CHEMSIM_LBM_NCCL_ID_BYTES 128
 
@@ -129,6 +129,18 @@ typedef struct {
 int chemsim_lbm_slab_rows(int global_height, int rank, int nranks, int *row_offset, int *rows);
 int chemsim_lbm_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out, int *count);
 
+/* Device-side barrier over the ranks of a sharded lattice: a one-element ncclAllReduce queued on
+ * the handle's stream (asynchronous for the host).  Work queued after it starts on every rank at
+ * the same time to within a collective's latency — what a multi-GPU timing needs before its start
+ * event.  No-op for an unsharded lattice.  COLLECTIVE. */
+int chemsim_lbm_barrier(chemsim_lbm_t *h);
+
+/* How long a face block of the peer-memory halo waits for a neighbour's step flag before it gives
+ * up (default 30 s, or CHEMSIM_LBM_P2P_TIMEOUT_S).  After a time-out the lattice is poisoned: the
+ * rank stops publishing its steps, and chemsim_lbm_step, _synchronize and every readout return
+ * CHEMSIM_LBM_ERR_CUDA until new populations are uploaded on every rank. */
+int chemsim_lbm_set_p2p_timeout(chemsim_lbm_t *h, double seconds);
+
 int chemsim_lbm_destroy(chemsim_lbm_t *h); /* Drop for State */
 
 /* State::size (src/lbm.rs:753-756) and the slab this handle owns. */
@@ -191,6 +203,17 @@ int chemsim_lbm_set_geometry_rows(chemsim_lbm_t *h, int row_begin, int row_count
  * for it on the device, the host does not block. */
 int chemsim_lbm_set_geometry_async(chemsim_lbm_t *h, const uint8_t *solid, size_t n);
 
+/* Live geometry edits on the device.  The reference's mouse handler
+ * (src/main.rs:71-91) downloads the mask, rewrites EVERY cell on the host — solid iff
+ * |row - floor(pos[1])| < 5 and |col - floor(pos[0])| < 5 — and uploads it again; here that is
+ * chemsim_lbm_fill_geometry(h, 0) followed by chemsim_lbm_paint_rect(h, px-4, py-4, 9, 9, 1): two
+ * small kernels on the handle's stream, no host transfer.  Both are asynchronous.
+ * paint_rect: cells [x0, x0+width) x [y0, y0+height) := value != 0; y is a GLOBAL row, the
+ * rectangle is clipped to the lattice and to this handle's slab (on a sharded lattice every rank
+ * makes the same call and paints its part). */
+int chemsim_lbm_fill_geometry(chemsim_lbm_t *h, int value);
+int chemsim_lbm_paint_rect(chemsim_lbm_t *h, int x0, int y0, int width, int height, int value);
+
 /* ---- the hot path --------------------------------------------------------- */
 
 /* State::step x nsteps (src/lbm.rs:694-714): stream -> bounce_back -> collide
@@ -209,6 +232,22 @@ int chemsim_lbm_get_density(chemsim_lbm_t *h, void *dst, size_t n);          /* 
  * to page-locked `dst` on a separate stream while later steps run; `dst` is valid
  * after chemsim_lbm_synchronize().  At most two snapshots are in flight. */
 int chemsim_lbm_get_density_async(chemsim_lbm_t *h, void *dst, size_t n);
+/* The same for every readout main.rs's four display modes use (src/main.rs:157-174) and the rest
+ * of the surface: field selects the getter, q the population for the per-direction fields, dst1
+ * is the second component of VELOCITY / MOMENTUM_DENSITY and NULL otherwise.  This is what a
+ * recorder (src/display.rs:157-185 steps and renders every frame) calls so that the transfer of
+ * frame n overlaps the steps of frame n+1. */
+typedef enum {
+    CHEMSIM_LBM_FIELD_DENSITY = 0,          /* State::density          src/lbm.rs:779 */
+    CHEMSIM_LBM_FIELD_PRESSURE = 1,         /* State::pressure         :784 */
+    CHEMSIM_LBM_FIELD_SPEED = 2,            /* State::speed            :800 */
+    CHEMSIM_LBM_FIELD_VELOCITY = 3,         /* State::velocity         :795 (dst0 = x, dst1 = y) */
+    CHEMSIM_LBM_FIELD_MOMENTUM_DENSITY = 4, /* State::momentum_density :790 (dst0 = x, dst1 = y) */
+    CHEMSIM_LBM_FIELD_POPULATION = 5,       /* State::populations      :769, direction q */
+    CHEMSIM_LBM_FIELD_EQUILIBRIUM = 6,      /* State::equilibrium      :805, direction q */
+    CHEMSIM_LBM_FIELD_NON_EQUILIBRIUM = 7   /* State::non_equilibrium  :810, direction q */
+} chemsim_lbm_field;
+int chemsim_lbm_get_async(chemsim_lbm_t *h, int field, int q, void *dst0, void *dst1, size_t n);
 int chemsim_lbm_get_pressure(chemsim_lbm_t *h, void *dst, size_t n);         /* State::pressure :784          */
 int chemsim_lbm_get_speed(chemsim_lbm_t *h, void *dst, size_t n);            /* State::speed    :800 -> :151 */
 int chemsim_lbm_get_velocity(chemsim_lbm_t *h, void *vx, void *vy, size_t n);         /* :795 -> :133 */
@@ -237,6 +276,30 @@ int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t
 
 /* State::is_unstable (src/lbm.rs:815-818): min(f_eq,0) < 0 on this handle's cells. */
 int chemsim_lbm_is_unstable(chemsim_lbm_t *h, int *out);
+
+/* ---- checkpoint / restore ---------------------------------- */
+
+/* A State as bytes: header, the nine populations of this handle's slab as dense row-major planes
+ * in the lattice dtype (what State::populations + get_underlying would give, src/lbm.rs:769,
+ * src/matrix.rs:120-126), then the geometry (one byte per cell).  The reference has no
+ * serialisation; its recorder (src/display.rs:157-185, dead src/record.rs) only keeps rendered
+ * frames.  restore() checks dtype / shape / slab, uploads populations and geometry and sets
+ * state.time and the step counter; the collision operator and the discretization are recorded in
+ * the header for the caller but NOT applied (the host State owns them).  On a sharded lattice
+ * every rank checkpoints / restores its own slab; the first step after a restore re-exchanges the
+ * halo, so restore is collective in the same sense as an upload. */
+#define CHEMSIM_LBM_CHECKPOINT_MAGIC "CSLBMCK1"
+typedef struct {
+    char magic[8];
+    uint32_t header_bytes, dtype, width, local_height, global_height, row_offset, rank, nranks, edge, collision;
+    uint32_t step_index;
+    float time_f32;           /* state.time as accumulated in f32 (the reference's Scalar) */
+    double time_f64;          /* ... and in f64 (the value an F64 lattice reports) */
+    double delta_x, delta_t, tau, tau_plus, tau_minus, viscosity;
+} chemsim_lbm_checkpoint_header;
+int chemsim_lbm_checkpoint_bytes(const chemsim_lbm_t *h, size_t *out);
+int chemsim_lbm_checkpoint(chemsim_lbm_t *h, void *dst, size_t bytes);
+int chemsim_lbm_restore(chemsim_lbm_t *h, const void *src, size_t bytes);
 
 /* ---- interop / introspection ---------------------------------------------- */
 

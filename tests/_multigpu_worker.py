@@ -51,6 +51,23 @@ def main():
     dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
     images = [None] * world
     dist.gather_object(image, images if rank == 0 else None, dst=0)
+    # f-3 / f-4 on a sharded lattice: every rank paints the same GLOBAL rectangle (it straddles a
+    # slab face: rows around hg/2 and around the lattice's first rows), checkpoints, steps, restores
+    # and replays; rank 0 compares with the oracle run on the host-edited mask.
+    ry, rh = max(0, hg // 2 - 3), min(7, hg)
+    state.paint_rect(w // 4, ry, max(1, w // 2), rh, True)
+    state.paint_rect(-3, -2, 9, 4, True)
+    state.step(2)
+    blob = state.checkpoint()
+    state.step(3)
+    first = state.populations_array()
+    state.restore(blob)
+    state.step(3)
+    state.synchronize()
+    again = state.populations_array()
+    replay_ok = bool((first.view(np.uint8) == again.view(np.uint8)).all()) and abs(state.time - (steps + 5)) < 1e-6
+    painted = [None] * world
+    dist.gather_object((again, state.geometry, replay_ok), painted if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
         got = np.concatenate(gathered, axis=1)
@@ -67,6 +84,13 @@ def main():
         whole = single.render(single.RENDER_SPEED).astype(np.int16)
         ok = ok and int(np.abs(np.concatenate(images, axis=0).astype(np.int16) - whole).max()) <= 1
         ok = ok and abs(mass - O.total_mass(ref)) <= 1e-12 * abs(mass)
+        solid2 = solid.copy()
+        solid2[ry:ry + rh, w // 4:w // 4 + max(1, w // 2)] = 1
+        solid2[0:2, 0:6] = 1
+        ref2 = O.step_fused(ref, solid2, 5, 0.8, edge)
+        ok = ok and all(p[2] for p in painted)
+        ok = ok and bool((np.concatenate([p[1] for p in painted], axis=0) == solid2.astype(bool)).all())
+        ok = ok and bool((np.concatenate([p[0] for p in painted], axis=1).view(u) == ref2.view(u)).all())
         ok = ok and abs(m0 - O.total_mass(f0)) <= 1e-12 * abs(m0)
         print(("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH") + f" world={world} {w}x{hg} edge={edge} {dtype_name} halo={halo}", flush=True)
     state.close()

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = C.CDLL(_ffi.LIB_PATH)
     for name in declared_symbols():
         assert getattr(raw, name) is not None
-    assert lib.chemsim_lbm_abi_version() == 1
+    assert lib.chemsim_lbm_abi_version() == _ffi.ABI_VERSION == 2
 
 
 def test_no_oracle_in_the_product_path():

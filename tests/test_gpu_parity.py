@@ -454,3 +454,166 @@ def test_large_lattice_16384_needs_64bit_offsets():
         assert got[h - 1, w - 1] == got[0, 0]
     assert abs(state.total_mass() - mass0) <= 2e-7 * mass0      # ~10 steps of the (sum w - 1)/tau drift
     state.close()
+
+
+# ---- live geometry edit on the device, async snapshots of every field, checkpoints (f-3, f-4) ----
+
+def brush_mask(w, h, pos):
+    """The reference's mouse handler, literally (src/main.rs:71-91): EVERY cell is rewritten;
+    solid iff |a - x| < 5 and |b - y| < 5 with x = floor(pos[1]), y = floor(pos[0]); a indexes
+    rows (dim0), b columns (dim1) of the square geometry array."""
+    x, y = int(np.floor(pos[1])), int(np.floor(pos[0]))
+    a = np.arange(h)[:, None]
+    b = np.arange(w)[None, :]
+    return ((np.abs(a - x) < 5) & (np.abs(b - y) < 5)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_paint_brush_on_the_device_equals_the_host_rewrite(dtype):
+    w = h = 192
+    rho, vx, vy, solid = scenarios.main_rs(w, h, dtype, walls=True, radius=20.0)
+    state = make_state(rho, vx, vy, solid, 0.8, lbm.EDGE_ZEROFILL, dtype)
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    state.step(2)
+    f_ref = O.step_fused(f_ref, solid, 2, 0.8, O.EDGE_ZEROFILL)
+    # interior, clipped at the left/top edge, clipped at the right/bottom edge, outside (ignored)
+    for pos in ((100.7, 50.2), (1.0, 2.9), (190.5, 191.0), (500.0, 10.0)):
+        state.paint_brush(pos)
+        inside = 0 <= int(pos[1]) < h and 0 <= int(pos[0]) < w            # main.rs:76
+        if inside:
+            solid = brush_mask(w, h, pos)
+        np.testing.assert_array_equal(state.geometry, solid.astype(bool))
+        state.step(3)
+        f_ref = O.step_fused(f_ref, solid, 3, 0.8, O.EDGE_ZEROFILL)
+        assert_parity(state.populations_array(), f_ref, f"after brush at {pos}")
+    # erase with a rectangle, add a wide one that crosses many flag segments
+    state.paint_rect(0, 0, w, h, False)
+    state.paint_rect(-7, 100, 150, 3, True)
+    solid = np.zeros((h, w), np.uint8)
+    solid[100:103, 0:143] = 1
+    np.testing.assert_array_equal(state.geometry, solid.astype(bool))
+    state.step(4)
+    f_ref = O.step_fused(f_ref, solid, 4, 0.8, O.EDGE_ZEROFILL)
+    assert_parity(state.populations_array(), f_ref, "after paint_rect")
+    state.fill_geometry(False)
+    state.step(2)
+    f_ref = O.step_fused(f_ref, np.zeros_like(solid), 2, 0.8, O.EDGE_ZEROFILL)
+    assert_parity(state.populations_array(), f_ref, "after fill_geometry(False)")
+    assert "vec" in state.step_kernel_name()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_async_snapshots_of_every_field(dtype):
+    """chemsim_lbm_get_async for all of main.rs's display modes (main.rs:157-174) and the rest of
+    the readout surface: snapshots queued between steps, read after one synchronize."""
+    import torch
+    from chemsim_b200 import _ffi
+    w, h = 260, 33
+    rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=61, solid_fraction=0.05)
+    state = make_state(rho, vx, vy, solid, 0.9, lbm.EDGE_PERIODIC, dtype)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    buf = lambda: torch.empty((h, w), dtype=tdt).pin_memory()
+    f_ref = O.compute_equilibrium(rho, vx, vy)
+    step_ref = lambda f, n: O.step_fused(f, solid, n, 0.9, O.EDGE_PERIODIC)
+
+    # (field, q, reference) for two snapshots in flight at a time, steps in between
+    state.step(2); f_ref = step_ref(f_ref, 2)
+    a0, a1 = buf(), buf()
+    state.get_async(_ffi.FIELD_VELOCITY, a0.data_ptr(), a0.numel(), a1.data_ptr())
+    want_v = O.velocity(f_ref)
+    state.step(1); f_ref = step_ref(f_ref, 1)
+    b0 = buf()
+    state.get_async(_ffi.FIELD_SPEED, b0.data_ptr(), b0.numel())
+    want_s = O.speed(f_ref)
+    state.step(3); f_ref = step_ref(f_ref, 3)
+    state.synchronize()
+    assert_parity(a0.numpy(), want_v[0], "async velocity x")
+    assert_parity(a1.numpy(), want_v[1], "async velocity y")
+    assert_parity(b0.numpy(), want_s, "async speed")
+
+    c0, c1, d0 = buf(), buf(), buf()
+    state.get_async(_ffi.FIELD_MOMENTUM_DENSITY, c0.data_ptr(), c0.numel(), c1.data_ptr())
+    want_m = O.momentum_density(f_ref)
+    state.get_async(_ffi.FIELD_POPULATION, d0.data_ptr(), d0.numel(), q=7)
+    want_p = f_ref[7].copy()
+    state.step(2); f_ref = step_ref(f_ref, 2)             # the lattice buffer the snapshot came from is rewritten
+    state.synchronize()
+    assert_parity(c0.numpy(), want_m[0], "async momentum x")
+    assert_parity(c1.numpy(), want_m[1], "async momentum y")
+    assert_parity(d0.numpy(), want_p, "async population 7")
+
+    e0, g0 = buf(), buf()
+    state.get_async(_ffi.FIELD_PRESSURE, e0.data_ptr(), e0.numel())
+    state.get_async(_ffi.FIELD_NON_EQUILIBRIUM, g0.data_ptr(), g0.numel(), q=3)
+    state.synchronize()
+    assert_parity(e0.numpy(), O.pressure(f_ref), "async pressure")
+    assert_parity(g0.numpy(), f_ref[3] - O.lattice_equilibrium(f_ref)[3], "async non-equilibrium 3")
+    h0 = buf()
+    state.get_async(_ffi.FIELD_EQUILIBRIUM, h0.data_ptr(), h0.numel(), q=5)
+    state.get_async(_ffi.FIELD_DENSITY, e0.data_ptr(), e0.numel())
+    state.synchronize()
+    assert_parity(h0.numpy(), O.lattice_equilibrium(f_ref)[5], "async equilibrium 5")
+    assert_parity(e0.numpy(), O.density(f_ref), "async density")
+    with pytest.raises(lbm.LbmError):
+        state.get_async(_ffi.FIELD_VELOCITY, a0.data_ptr(), a0.numel())          # second component missing
+    with pytest.raises(lbm.LbmError):
+        state.get_async(_ffi.FIELD_DENSITY, a0.data_ptr(), a0.numel(), a1.data_ptr())
+    with pytest.raises(lbm.LbmError):
+        state.get_async(_ffi.FIELD_POPULATION, a0.data_ptr(), a0.numel(), q=9)
+    assert_parity(state.populations_array(), f_ref, "populations after the async readouts")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_checkpoint_restore_round_trip(dtype):
+    w, h = 132, 29
+    rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=71)
+    state = make_state(rho, vx, vy, solid, 0.8, lbm.EDGE_PERIODIC, dtype)
+    state.step(5)
+    blob = state.checkpoint()
+    hdr = blob[:8].tobytes()
+    header_bytes = int(blob[8:12].view(np.uint32)[0])
+    assert hdr == b"CSLBMCK1" and header_bytes == 112
+    assert blob.size == header_bytes + 9 * w * h * np.dtype(dtype).itemsize + w * h
+    assert int(blob[48:52].view(np.uint32)[0]) == 5                        # step_index
+    f5 = state.populations_array()
+    state.step(7)
+    f12 = state.populations_array()
+    t12 = state.time
+    # restore into the same handle: back to step 5, then the same 7 steps again
+    state.restore(blob)
+    assert abs(state.time - 5.0) < 1e-6
+    assert_parity(state.populations_array(), f5, "restored populations")
+    np.testing.assert_array_equal(state.geometry, solid.astype(bool))
+    state.step(7)
+    assert_parity(state.populations_array(), f12, "replayed steps")
+    assert state.time == t12
+    # ... and into a fresh handle with a different geometry/populations
+    other = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
+    other.restore(blob.tobytes())
+    other.step(7)
+    assert_parity(other.populations_array(), f12, "fresh handle")
+    f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), solid, 12, 0.8, O.EDGE_PERIODIC)
+    assert_parity(f12, f_ref, "oracle")
+    # a checkpoint of another lattice is refused
+    wrong = lbm.State.create((w, h + 1), lbm.BGK(0.8), dtype=dtype)
+    with pytest.raises(lbm.LbmError):
+        wrong.restore(blob)
+    with pytest.raises(lbm.LbmError):
+        other.restore(blob[:200].copy())
+    bad = blob.copy(); bad[0] = 0
+    with pytest.raises(lbm.LbmError):
+        other.restore(bad)
+
+
+def test_regularized_reports_the_underlying_viscosity_with_the_state_discretization():
+    """Regularized::kinematic_shear_viscosity(disc) = underlying.kinematic_shear_viscosity(disc)
+    (src/lbm.rs:663-665) — with the State's dx/dt, not the unit discretization."""
+    import ctypes as C
+    from chemsim_b200 import _ffi
+    disc = lbm.Discretization(0.5, 0.25)
+    op = lbm.Regularized.new(lbm.BGK(0.9))
+    state = lbm.State.create((16, 4), op, disc, dtype=np.float32)
+    out = C.c_double()
+    _ffi.check(_ffi.load().chemsim_lbm_kinematic_shear_viscosity(state._h, C.byref(out)), state._h)
+    assert np.float32(out.value) == lbm.BGK(0.9).kinematic_shear_viscosity(disc, np.float32)
+    assert _ffi.load().chemsim_lbm_kinematic_bulk_viscosity(state._h, None) == _ffi.ERR_INVALID_ARGUMENT
