@@ -593,7 +593,7 @@ def throughput_record(ctx, args, workload, steps, reps, warmup=3, mass_check=Fal
         remember_n1(args.dtype, workload, glups)
     if n1:
         rec["n1_value"] = n1
-        rec["efficiency"] = glups / (n1 if scaling == "strong" else n1 * world) if world > 1 else 1.0
+        rec["efficiency"] = glups / (n1 * world)          # strong and weak alike: GLUPS_N / (N * GLUPS_1)
         rec["efficiency_basis"] = "same-box N=1 run of this bench (%s)" % N1_RECORD
     return rec
 
