@@ -6,6 +6,8 @@
 //  step_bgk.cu / step_trt.cu / step_regularized.cu / step_kbc.cu.
 //  Here: readout / mass / unstable / init kernels for the macroscopic surface of lbm.rs
 //  (:117-160, :779-818, :43-71), the segment flags of the geometry mask, the device-side render.
+#include <cstdlib>
+
 #include "step_decl.cuh"
 
 namespace chemsim {
@@ -359,6 +361,31 @@ int launch_step(const StepArgs<T> &a, cudaStream_t s)
     return e ? e : 1;
 }
 
+// Two steps per pass: vector widths only; the tile machinery pays off from a few tile rows on
+// (CHEMSIM_LBM_STEP2=0 in the environment keeps every step on the single-step kernels).
+template <typename T>
+bool step2_supported(const StepArgs<T> &a)
+{
+    static const bool on = [] { const char *e = getenv("CHEMSIM_LBM_STEP2"); return !(e && e[0] == '0'); }();
+    return on && use_vec(a) && a.H >= 4 && a.W >= 4 * VecOf<T>::N;
+}
+
+template <typename T>
+int launch_step2(const StepArgs<T> &a, cudaStream_t s)
+{
+    if (a.y_count <= 0) return 0;
+    if (!use_vec(a)) return -(int)cudaErrorInvalidValue;
+    switch (a.collision) {
+    case COL_BGK:         launch_step2_col<T, COL_BGK>(a, s); break;
+    case COL_TRT:         launch_step2_col<T, COL_TRT>(a, s); break;
+    case COL_REGULARIZED: launch_step2_col<T, COL_REGULARIZED>(a, s); break;
+    case COL_KBC:         launch_step2_col<T, COL_KBC>(a, s); break;
+    default: return -(int)cudaErrorInvalidValue;
+    }
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
 template <typename T>
 int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane, int pitch, int W,
                             int row_begin, int rows, const Consts<T> &k, cudaStream_t s)
@@ -450,6 +477,8 @@ int launch_paint_rect(uint8_t *mask, int mask_pitch, int x0, int y0, int w, int 
 
 #define CHEMSIM_INSTANTIATE(T)                                                                                       \
     template int launch_step<T>(const StepArgs<T> &, cudaStream_t);                                                  \
+    template int launch_step2<T>(const StepArgs<T> &, cudaStream_t);                                                 \
+    template bool step2_supported<T>(const StepArgs<T> &);                                                           \
     template int launch_face_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \
     template bool face_p2p_supported<T>(const StepArgs<T> &);                                                        \
     template int launch_slab_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \

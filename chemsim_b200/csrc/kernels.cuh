@@ -35,6 +35,9 @@ struct StepArgs {
     int y_begin, y_count;  // this launch updates rows y_begin + i*y_stride, i in [0, y_count)
     int y_stride;          // 1 for a band of rows; H−1 for the two face rows {0, H−1} of a slab
     int xchunks;           // blocks per row (set by the launcher): block b works on chunk b % xchunks of row group b / xchunks
+    int ghost;             // ghost rows above and below the slab in the layout (row y lives at plane row y + ghost)
+    int row0, Hglobal;     // this slab's first global row and the global height (zero-fill: what lies outside)
+    int periodic_y;        // 1: the lattice is periodic in y (sharded: the ghost rows carry the wrap)
     int wrap_y;            // 1: rows −1/H alias rows H−1/0 (periodic, unsharded); 0: read the ghost rows
     int periodic_x;        // 1: wrap in x; 0: zero-fill (reference)
     const uint8_t *mask;   // H rows of mask_pitch bytes, non-zero = solid
@@ -82,6 +85,9 @@ struct ReadoutArgs {
 // Each launcher returns the number of kernels it launched (for the handle's
 // launch counter) or a negative cudaError_t.
 template <typename T> int launch_step(const StepArgs<T> &a, cudaStream_t s);
+// the same rows advanced by TWO steps in one pass (temporal blocking through shared memory, step2_impl.cuh)
+template <typename T> int launch_step2(const StepArgs<T> &a, cudaStream_t s);
+template <typename T> bool step2_supported(const StepArgs<T> &a);
 template <typename T> const char *step_kernel_name(const StepArgs<T> &a);
 // the two face rows + the halo stores into the neighbours' ghost rows, one kernel (vector widths only)
 template <typename T> int launch_face_p2p(const StepArgs<T> &a, cudaStream_t s);

@@ -160,6 +160,10 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.y_count = y_count;
     a.y_stride = y_stride;
     a.xchunks = 1;
+    a.ghost = 1;
+    a.row0 = h->row0;
+    a.Hglobal = h->Hglobal;
+    a.periodic_y = h->edge == CHEMSIM_LBM_EDGE_PERIODIC ? 1 : 0;
     a.wrap_y = (h->edge == CHEMSIM_LBM_EDGE_PERIODIC && h->nranks == 1) ? 1 : 0;
     a.periodic_x = h->edge == CHEMSIM_LBM_EDGE_PERIODIC ? 1 : 0;
     a.mask = h->mask;
@@ -447,7 +451,15 @@ int step_impl(chemsim_lbm *h, int nsteps)
 {
     if (nsteps == 0) return 0;
     if (h->nranks == 1) {
-        for (int s = 0; s < nsteps; ++s) {
+        int left = nsteps;
+        // pairs of steps in one pass over HBM (temporal blocking, step2_impl.cuh); an odd step on its own
+        while (left >= 2 && step2_supported(step_args<T>(h, 0, h->H))) {
+            LAUNCH_TRY(h, launch_step2<T>(step_args<T>(h, 0, h->H), h->stream));
+            h->cur ^= 1;
+            h->step_index += 2;
+            left -= 2;
+        }
+        for (; left > 0; --left) {
             LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H), h->stream));
             h->cur ^= 1;
             h->step_index += 1;

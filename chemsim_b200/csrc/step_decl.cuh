@@ -30,5 +30,6 @@ inline bool use_vec(const StepArgs<T> &a) { return a.W % VecOf<T>::N == 0; }
 template <typename T, int COL> void launch_step_col(const StepArgs<T> &a, cudaStream_t s);
 template <typename T, int COL> void launch_slab_p2p_col(const StepArgs<T> &a, cudaStream_t s);
 template <typename T, int COL> void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s);
+template <typename T, int COL> void launch_step2_col(const StepArgs<T> &a, cudaStream_t s);
 
 }  // namespace chemsim

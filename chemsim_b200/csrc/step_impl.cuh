@@ -388,11 +388,12 @@ static inline bool pdl_enabled()
 }
 
 template <typename T>
-static void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cudaStream_t s, const StepArgs<T> &a)
+static void launch_chained(void (*kernel)(const StepArgs<T>), dim3 grid, dim3 block, cudaStream_t s, const StepArgs<T> &a,
+                           size_t smem = 0)
 {
-    if (!pdl_enabled()) { kernel<<<grid, block, 0, s>>>(a); return; }
+    if (!pdl_enabled()) { kernel<<<grid, block, smem, s>>>(a); return; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -514,7 +515,15 @@ void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s)
     }
 }
 
+}  // namespace chemsim
+
+#include "step2_impl.cuh"
+
+namespace chemsim {
+
 #define CHEMSIM_INSTANTIATE_STEP(COL)                                                              \
+    template void launch_step2_col<float, COL>(const StepArgs<float> &, cudaStream_t);             \
+    template void launch_step2_col<double, COL>(const StepArgs<double> &, cudaStream_t);           \
     template void launch_step_col<float, COL>(const StepArgs<float> &, cudaStream_t);              \
     template void launch_step_col<double, COL>(const StepArgs<double> &, cudaStream_t);            \
     template void launch_slab_p2p_col<float, COL>(const StepArgs<float> &, cudaStream_t);          \
