@@ -99,10 +99,11 @@ class HaloMsg(C.Structure):
     _fields_ = [("is_send", C.c_int), ("peer", C.c_int), ("q", C.c_int), ("row", C.c_int)]
 
 
-HALO_PLAN_MAX = 12
-ROW_FIRST, ROW_LAST, ROW_GHOST_ABOVE, ROW_GHOST_BELOW = range(4)
+HALO_PLAN_MAX = 48
+(ROW_FIRST, ROW_LAST, ROW_GHOST_ABOVE, ROW_GHOST_BELOW, ROW_SECOND, ROW_SECOND_LAST, ROW_GHOST_ABOVE2,
+ ROW_GHOST_BELOW2) = range(8)
 PROTOTYPES["chemsim_lbm_slab_rows"] = (_I, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I)])
-PROTOTYPES["chemsim_lbm_halo_plan"] = (_I, [_I, _I, _I, C.POINTER(HaloMsg), C.POINTER(_I)])
+PROTOTYPES["chemsim_lbm_halo_plan"] = (_I, [_I, _I, _I, _I, C.POINTER(HaloMsg), C.POINTER(_I)])
 
 _lib = None
 

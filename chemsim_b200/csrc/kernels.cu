@@ -28,7 +28,7 @@ __global__ void init_equilibrium_kernel(const T *rho, const T *vx, const T *vy, 
     const T v2 = add(mul(ux, ux), mul(uy, uy));
 #pragma unroll
     for (int q = 0; q < Q; ++q)
-        dst[(size_t)q * plane + (size_t)(y + 1) * pitch + x] = equilibrium_i(q, r, ux, uy, v2, k);
+        dst[(size_t)q * plane + (size_t)(y + GHOST) * pitch + x] = equilibrium_i(q, r, ux, uy, v2, k);
 }
 
 // ---- macroscopic readout (src/lbm.rs:117-173, :779-812) ----------------------
@@ -40,7 +40,7 @@ __global__ void readout_kernel(const __grid_constant__ ReadoutArgs<T> a)
     if (x >= a.W || y >= a.H) return;
     T g[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) g[q] = a.src[(size_t)q * a.plane + (size_t)(y + 1) * a.pitch + x];
+    for (int q = 0; q < Q; ++q) g[q] = a.src[(size_t)q * a.plane + (size_t)(y + GHOST) * a.pitch + x];
     const size_t c = (size_t)y * a.W + x;
     switch (a.kind) {
     case READ_DENSITY:  a.out0[c] = density(g); break;
@@ -101,7 +101,7 @@ mass_partial_kernel(const T *src, size_t plane, int pitch, int W, int H, double 
     const size_t cells = (size_t)W * H;
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x) {
         const int y = (int)(c / W), x = (int)(c % W);
-        const T *p = src + (size_t)(y + 1) * pitch + x;
+        const T *p = src + (size_t)(y + GHOST) * pitch + x;
         double cell = 0.0;
 #pragma unroll
         for (int q = 0; q < Q; ++q) cell += (double)p[(size_t)q * plane];
@@ -131,7 +131,7 @@ unstable_kernel(const T *src, size_t plane, int pitch, int W, int H, const __gri
         const int y = (int)(c / W), x = (int)(c % W);
         T g[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + 1) * pitch + x];
+        for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + GHOST) * pitch + x];
         const Moments<T> m = moments(g);
         const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));
         bad |= equilibrium_i(0, m.rho, m.vx, m.vy, v2, k) < T(0);
@@ -198,7 +198,7 @@ render_stats_partial_kernel(const T *src, size_t plane, int pitch, int W, int H,
         const int y = (int)(c / W), x = (int)(c % W);
         T g[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + 1) * pitch + x];
+        for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + GHOST) * pitch + x];
         float vx, vy;
         const double v = (double)render_scalar(g, mode, vx, vy);
         s1 += v; s2 += v * v;
@@ -262,7 +262,7 @@ __global__ void render_image_kernel(const T *src, size_t plane, int pitch, int W
     if (x >= W || y >= H) return;
     T g[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + 1) * pitch + x];
+    for (int q = 0; q < Q; ++q) g[q] = src[(size_t)q * plane + (size_t)(y + GHOST) * pitch + x];
     float vx, vy;
     const float field = render_scalar(g, mode, vx, vy);
     const float avg = (float)stats[0], inv_std = 1.0f / (float)stats[1];      // `avg as f32`, `1.0 / std as f32`
@@ -310,7 +310,7 @@ const char *step_kernel_name(const StepArgs<T> &a)
 template <typename T>
 bool slab_p2p_supported(const StepArgs<T> &a)
 {
-    return use_vec(a) && a.W / VecOf<T>::N >= STEP_THREADS;
+    return use_vec(a) && a.W / VecOf<T>::N >= STEP_THREADS && a.H >= 4;
 }
 
 template <typename T>
@@ -322,24 +322,6 @@ int launch_slab_p2p(const StepArgs<T> &a, cudaStream_t s)
     case COL_TRT:         launch_slab_p2p_col<T, COL_TRT>(a, s); break;
     case COL_REGULARIZED: launch_slab_p2p_col<T, COL_REGULARIZED>(a, s); break;
     case COL_KBC:         launch_slab_p2p_col<T, COL_KBC>(a, s); break;
-    default: return -(int)cudaErrorInvalidValue;
-    }
-    const int e = check_launch();
-    return e ? e : 1;
-}
-
-template <typename T>
-bool face_p2p_supported(const StepArgs<T> &a) { return use_vec(a); }
-
-template <typename T>
-int launch_face_p2p(const StepArgs<T> &a, cudaStream_t s)
-{
-    if (a.y_count <= 0 || !use_vec(a)) return -(int)cudaErrorInvalidValue;
-    switch (a.collision) {
-    case COL_BGK:         launch_face_p2p_col<T, COL_BGK>(a, s); break;
-    case COL_TRT:         launch_face_p2p_col<T, COL_TRT>(a, s); break;
-    case COL_REGULARIZED: launch_face_p2p_col<T, COL_REGULARIZED>(a, s); break;
-    case COL_KBC:         launch_face_p2p_col<T, COL_KBC>(a, s); break;
     default: return -(int)cudaErrorInvalidValue;
     }
     const int e = check_launch();
@@ -367,7 +349,24 @@ template <typename T>
 bool step2_supported(const StepArgs<T> &a)
 {
     static const bool on = [] { const char *e = getenv("CHEMSIM_LBM_STEP2"); return !(e && e[0] == '0'); }();
-    return on && use_vec(a) && a.H >= 4 && a.W >= 4 * VecOf<T>::N;
+    return on && a.collision != COL_KBC && use_vec(a) && a.H >= 4 && a.W >= 4 * VecOf<T>::N;
+}
+
+template <typename T>
+int step2_tile_rows() { return Step2Tile<T>::TY; }
+
+template <typename T>
+int launch_slab_p2p2(const StepArgs<T> &a, cudaStream_t s)
+{
+    if (!slab_p2p_supported(a) || a.H < 2 * Step2Tile<T>::TY) return -(int)cudaErrorInvalidValue;
+    switch (a.collision) {
+    case COL_BGK:         launch_slab_p2p2_col<T, COL_BGK>(a, s); break;
+    case COL_TRT:         launch_slab_p2p2_col<T, COL_TRT>(a, s); break;
+    case COL_REGULARIZED: launch_slab_p2p2_col<T, COL_REGULARIZED>(a, s); break;
+    default: return -(int)cudaErrorInvalidValue;
+    }
+    const int e = check_launch();
+    return e ? e : 1;
 }
 
 template <typename T>
@@ -379,7 +378,6 @@ int launch_step2(const StepArgs<T> &a, cudaStream_t s)
     case COL_BGK:         launch_step2_col<T, COL_BGK>(a, s); break;
     case COL_TRT:         launch_step2_col<T, COL_TRT>(a, s); break;
     case COL_REGULARIZED: launch_step2_col<T, COL_REGULARIZED>(a, s); break;
-    case COL_KBC:         launch_step2_col<T, COL_KBC>(a, s); break;
     default: return -(int)cudaErrorInvalidValue;
     }
     const int e = check_launch();
@@ -479,8 +477,8 @@ int launch_paint_rect(uint8_t *mask, int mask_pitch, int x0, int y0, int w, int 
     template int launch_step<T>(const StepArgs<T> &, cudaStream_t);                                                  \
     template int launch_step2<T>(const StepArgs<T> &, cudaStream_t);                                                 \
     template bool step2_supported<T>(const StepArgs<T> &);                                                           \
-    template int launch_face_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \
-    template bool face_p2p_supported<T>(const StepArgs<T> &);                                                        \
+    template int launch_slab_p2p2<T>(const StepArgs<T> &, cudaStream_t);                                             \
+    template int step2_tile_rows<T>();                                                                               \
     template int launch_slab_p2p<T>(const StepArgs<T> &, cudaStream_t);                                              \
     template bool slab_p2p_supported<T>(const StepArgs<T> &);                                                        \
     template const char *step_kernel_name<T>(const StepArgs<T> &);                                                   \

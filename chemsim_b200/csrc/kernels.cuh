@@ -7,19 +7,28 @@
 namespace chemsim {
 
 // Device layout of one population set ("lattice buffer"):
-//   value of population q at local row y (−1 … H, the two extremes being ghost
-//   rows) and column x lives at  base[q*plane + (y+1)*pitch + x].
+//   value of population q at local row y (−GHOST … H+GHOST−1, the rows outside 0 … H−1 being
+//   ghost rows) and column x lives at  base[q*plane + (y+GHOST)*pitch + x].
+// Two ghost rows per side: a y-slab advances TWO steps per pass (step2_impl.cuh), which reads
+// the neighbour's two face rows; the single-step kernels only touch the inner ghost row.
+constexpr int GHOST = 2;
 // pitch is W rounded up to 128 bytes so every row starts on a cache line and
 // 128-bit vector accesses at x % VEC == 0 are aligned.
 // Peer-memory halo of a y-slab (filled in only for the P2P face kernel).
 struct HaloP2P {
-    void *up_dst = nullptr, *down_dst = nullptr;   // the neighbours' destination population buffers (peer-mapped)
+    // The neighbours' DESTINATION population buffers (peer-mapped).  A slab delivers, per step or
+    // double step, what the neighbour's next pass reads from its two ghost rows:
+    //   to the lower neighbour (larger y): my row H-1, all nine populations -> its ghost row -1,
+    //                                      my row H-2, the dy=+1 movers {3,6,7} -> its ghost row -2
+    //   to the upper neighbour:            my row 0, all nine -> its ghost row H_up,
+    //                                      my row 1, the dy=-1 movers {1,5,8} -> its ghost row H_up+1
+    void *up_dst = nullptr, *down_dst = nullptr;
     size_t up_plane = 0, down_plane = 0;           // their plane strides, in elements
-    int up_ghost_row = 0;                          // plane row of the upper neighbour's ghost row H (= H_up + 1)
+    int up_row0 = 0;                               // plane row of the upper neighbour's ghost row H_up (= H_up + GHOST)
     const unsigned *wait_up = nullptr, *wait_down = nullptr;   // local step flags the neighbours publish into
     unsigned *signal_up = nullptr, *signal_down = nullptr;     // the neighbours' flags this GPU publishes into
-    unsigned *done = nullptr;                      // local counter of finished blocks
-    unsigned step = 0;                             // t: needs flags >= t, publishes t+1
+    unsigned *done = nullptr;                      // local counter of finished face blocks
+    unsigned step = 0;                             // t: needs flags >= t, publishes t + (steps of this launch)
     int *error = nullptr;                          // device word: set to 1 if a wait timed out (sticky until re-upload)
     int *error_host = nullptr;                     // the same in mapped host memory, for the host API
     unsigned long long timeout_ns = 0;             // how long a face block waits for a neighbour's flag
@@ -43,6 +52,8 @@ struct StepArgs {
     const uint8_t *mask;   // H rows of mask_pitch bytes, non-zero = solid
     int mask_pitch;
     int has_mask;          // 0: no solid cell anywhere in this slab, mask not read
+    int ghost_mask;        // 1: a y-slab whose mask carries one halo row per side (the neighbour's face row, refreshed
+                           //    before every batch of steps): the two-step kernel applies it to ghost-row cells
     int collision;         // Collision enum: which CollisionOperator the step applies
     const uint8_t *mask_flags;  // per row, one byte per 64-cell segment: any solid cell in it?
     int flag_pitch;             // (a warp of the vector kernel covers whole segments and skips
@@ -89,12 +100,13 @@ template <typename T> int launch_step(const StepArgs<T> &a, cudaStream_t s);
 template <typename T> int launch_step2(const StepArgs<T> &a, cudaStream_t s);
 template <typename T> bool step2_supported(const StepArgs<T> &a);
 template <typename T> const char *step_kernel_name(const StepArgs<T> &a);
-// the two face rows + the halo stores into the neighbours' ghost rows, one kernel (vector widths only)
-template <typename T> int launch_face_p2p(const StepArgs<T> &a, cudaStream_t s);
-template <typename T> bool face_p2p_supported(const StepArgs<T> &a);
 // the whole slab (face rows first) + the halo stores + step flags in ONE launch per step
 template <typename T> int launch_slab_p2p(const StepArgs<T> &a, cudaStream_t s);
 template <typename T> bool slab_p2p_supported(const StepArgs<T> &a);
+// the same for TWO steps per launch (face tile rows first)
+template <typename T> int launch_slab_p2p2(const StepArgs<T> &a, cudaStream_t s);
+// rows a two-step pass needs at each face of a slab (the tile height of step2_impl.cuh)
+template <typename T> int step2_tile_rows();
 // rows [row_begin, row_begin + rows) of the lattice from dense (pitch == W) fields of `rows` rows
 template <typename T> int launch_init_equilibrium(const T *rho, const T *vx, const T *vy, T *dst, size_t plane,
                                                   int pitch, int W, int row_begin, int rows, const Consts<T> &k,

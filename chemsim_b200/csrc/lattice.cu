@@ -44,7 +44,8 @@ struct chemsim_lbm {
     int cur = 0;
     size_t plane = 0;   // elements
     int pitch = 0;      // elements
-    uint8_t *mask = nullptr;
+    uint8_t *mask_alloc = nullptr;   // H + 2 rows: one halo row above and below (a y-slab's neighbours' face rows)
+    uint8_t *mask = nullptr;         // row 0 of the slab inside mask_alloc
     int mask_pitch = 0;
     int has_mask = 0;          // 0 = known solid-free (mask never read); 1 = consult the segment flags
     uint8_t *mask_flags = nullptr;
@@ -139,8 +140,12 @@ void rebuild_scalars(chemsim_lbm *h)
 
 char *row_ptr(chemsim_lbm *h, int b, int q, int y)
 {
-    return (char *)h->buf[b] + ((size_t)q * h->plane + (size_t)(y + 1) * h->pitch) * h->esize;
+    return (char *)h->buf[b] + ((size_t)q * h->plane + (size_t)(y + GHOST) * h->pitch) * h->esize;
 }
+
+// two-row halo (all slabs have >= 2 rows) or the one-row form; see build_halo_plan
+bool deep_halo_of(int global_height, int nranks) { return nranks > 1 && global_height / nranks >= 2; }
+bool deep_halo(const chemsim_lbm *h) { return deep_halo_of(h->Hglobal, h->nranks); }
 
 template <typename T> const Consts<T> &consts_of(const chemsim_lbm *h);
 template <> const Consts<float> &consts_of<float>(const chemsim_lbm *h) { return h->k.f; }
@@ -160,7 +165,7 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.y_count = y_count;
     a.y_stride = y_stride;
     a.xchunks = 1;
-    a.ghost = 1;
+    a.ghost = GHOST;
     a.row0 = h->row0;
     a.Hglobal = h->Hglobal;
     a.periodic_y = h->edge == CHEMSIM_LBM_EDGE_PERIODIC ? 1 : 0;
@@ -169,6 +174,7 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.mask = h->mask;
     a.mask_pitch = h->mask_pitch;
     a.has_mask = h->has_mask;
+    a.ghost_mask = (h->nranks > 1 && deep_halo(h)) ? 1 : 0;
     a.collision = h->col.kind;
     a.mask_flags = h->mask_flags;
     a.flag_pitch = h->flag_pitch;
@@ -177,25 +183,51 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     return a;
 }
 
-// Halo plan: populations moving towards larger y (dy=+1: q = 3,6,7)
-// go from my last row to the lower neighbour's ghost row −1; populations moving
-// towards smaller y (dy=−1: q = 1,5,8) go from my first row to the upper
-// neighbour's ghost row H.  Sends are issued [to-lower, to-upper] and receives
-// [from-upper, from-lower], so that when both neighbours are the same rank
-// (nranks == 2, periodic) the k-th send to a peer matches its k-th receive.
-int build_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out)
+// Halo plan.  What a slab delivers per exchange is what the neighbour's next pass —
+// one step or two (step2_impl.cuh) — reads from its two ghost rows:
+//   to the lower neighbour (larger y): my last row, all nine populations -> its ghost row -1, and the
+//       dy=+1 movers q = 3,6,7 of my last-but-one row -> its ghost row -2;
+//   to the upper neighbour: my first row, all nine -> its ghost row H, and the dy=-1 movers q = 1,5,8 of
+//       my second row -> its ghost row H+1.
+// When some slab has a single row (global_height / nranks < 2) the plan is the one-row form (three
+// populations per face: all a single step needs) and two-step passes are off.
+// Sends are issued [to-lower, to-upper] and receives [from-upper, from-lower], so that when both
+// neighbours are the same rank (nranks == 2, periodic) the k-th send to a peer matches its k-th receive.
+int build_halo_plan(int global_height, int rank, int nranks, int edge, chemsim_lbm_halo_msg *out)
 {
     if (nranks <= 1) return 0;
-    const bool periodic = edge == CHEMSIM_LBM_EDGE_PERIODIC;
+    const bool periodic = edge == CHEMSIM_LBM_EDGE_PERIODIC, deep = deep_halo_of(global_height, nranks);
     const int up = (rank + nranks - 1) % nranks, down = (rank + 1) % nranks;
     const bool has_up = periodic || rank > 0, has_down = periodic || rank < nranks - 1;
     static const int to_down[3] = {3, 6, 7}, to_up[3] = {1, 5, 8};
     int n = 0;
-    if (has_down) for (int q : to_down) out[n++] = {1, down, q, CHEMSIM_LBM_ROW_LAST};
-    if (has_up)   for (int q : to_up)   out[n++] = {1, up, q, CHEMSIM_LBM_ROW_FIRST};
-    if (has_up)   for (int q : to_down) out[n++] = {0, up, q, CHEMSIM_LBM_ROW_GHOST_ABOVE};
-    if (has_down) for (int q : to_up)   out[n++] = {0, down, q, CHEMSIM_LBM_ROW_GHOST_BELOW};
+    auto face = [&](int is_send, int peer, int row_all, int row_movers, const int (&movers)[3]) {
+        if (deep) {
+            for (int q = 0; q < Q; ++q) out[n++] = {is_send, peer, q, row_all};
+            for (int q : movers) out[n++] = {is_send, peer, q, row_movers};
+        } else {
+            for (int q : movers) out[n++] = {is_send, peer, q, row_all};
+        }
+    };
+    if (has_down) face(1, down, CHEMSIM_LBM_ROW_LAST, CHEMSIM_LBM_ROW_SECOND_LAST, to_down);
+    if (has_up)   face(1, up, CHEMSIM_LBM_ROW_FIRST, CHEMSIM_LBM_ROW_SECOND, to_up);
+    if (has_up)   face(0, up, CHEMSIM_LBM_ROW_GHOST_ABOVE, CHEMSIM_LBM_ROW_GHOST_ABOVE2, to_down);
+    if (has_down) face(0, down, CHEMSIM_LBM_ROW_GHOST_BELOW, CHEMSIM_LBM_ROW_GHOST_BELOW2, to_up);
     return n;
+}
+
+int plan_row(const chemsim_lbm *h, int row)
+{
+    switch (row) {
+    case CHEMSIM_LBM_ROW_FIRST: return 0;
+    case CHEMSIM_LBM_ROW_SECOND: return 1;
+    case CHEMSIM_LBM_ROW_LAST: return h->H - 1;
+    case CHEMSIM_LBM_ROW_SECOND_LAST: return h->H - 2;
+    case CHEMSIM_LBM_ROW_GHOST_ABOVE: return -1;
+    case CHEMSIM_LBM_ROW_GHOST_ABOVE2: return -2;
+    case CHEMSIM_LBM_ROW_GHOST_BELOW: return h->H;
+    default: return h->H + 1;
+    }
 }
 
 // Rows of one population are contiguous, so the sends/receives work directly on
@@ -203,19 +235,40 @@ int build_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out)
 int exchange(chemsim_lbm *h, int b)
 {
     chemsim_lbm_halo_msg plan[CHEMSIM_LBM_HALO_PLAN_MAX];
-    const int count = build_halo_plan(h->rank, h->nranks, h->edge, plan);
+    const int count = build_halo_plan(h->Hglobal, h->rank, h->nranks, h->edge, plan);
     const size_t bytes = (size_t)h->W * h->esize;
     const NcclDyn &n = nccl_dyn();
     NCCL_TRY(h, n.GroupStart());
     for (int i = 0; i < count; ++i) {
         const chemsim_lbm_halo_msg &m = plan[i];
-        const int y = m.row == CHEMSIM_LBM_ROW_FIRST ? 0 : m.row == CHEMSIM_LBM_ROW_LAST ? h->H - 1
-                    : m.row == CHEMSIM_LBM_ROW_GHOST_ABOVE ? -1 : h->H;
+        const int y = plan_row(h, m.row);
         if (m.is_send) NCCL_TRY(h, n.Send(row_ptr(h, b, m.q, y), bytes, ncclChar, m.peer, h->comm, h->comm_stream));
         else           NCCL_TRY(h, n.Recv(row_ptr(h, b, m.q, y), bytes, ncclChar, m.peer, h->comm, h->comm_stream));
     }
     NCCL_TRY(h, n.GroupEnd());
     h->launches += 1;   // one fused NCCL send/recv kernel per group
+    return 0;
+}
+
+// The geometry's halo rows: my first / last mask row goes to the upper / lower neighbour's halo row
+// (what its two-step pass applies to the ghost-row cells it recomputes).  Runs before every batch of
+// steps — the mask may have been edited on any rank since the last one, and only a collective that
+// every rank always issues needs no agreement about that.
+int exchange_mask(chemsim_lbm *h)
+{
+    const bool periodic = h->edge == CHEMSIM_LBM_EDGE_PERIODIC;
+    const int up = (h->rank + h->nranks - 1) % h->nranks, down = (h->rank + 1) % h->nranks;
+    const bool has_up = periodic || h->rank > 0, has_down = periodic || h->rank < h->nranks - 1;
+    const NcclDyn &n = nccl_dyn();
+    uint8_t *first = h->mask, *last = h->mask + (size_t)(h->H - 1) * h->mask_pitch;
+    uint8_t *above = h->mask - h->mask_pitch, *below = h->mask + (size_t)h->H * h->mask_pitch;
+    NCCL_TRY(h, n.GroupStart());
+    if (has_down) NCCL_TRY(h, n.Send(last, h->W, ncclChar, down, h->comm, h->comm_stream));
+    if (has_up)   NCCL_TRY(h, n.Send(first, h->W, ncclChar, up, h->comm, h->comm_stream));
+    if (has_up)   NCCL_TRY(h, n.Recv(above, h->W, ncclChar, up, h->comm, h->comm_stream));
+    if (has_down) NCCL_TRY(h, n.Recv(below, h->W, ncclChar, down, h->comm, h->comm_stream));
+    NCCL_TRY(h, n.GroupEnd());
+    h->launches += 1;
     return 0;
 }
 
@@ -228,14 +281,14 @@ void fill_halo(const chemsim_lbm *h, HaloP2P &p)
     p = HaloP2P();
     if (has_up) {
         p.up_dst = h->peer_up_buf[b];
-        p.up_plane = (size_t)(h->peer_up_H + 2) * h->pitch;
-        p.up_ghost_row = h->peer_up_H + 1;
+        p.up_plane = (size_t)(h->peer_up_H + 2 * GHOST) * h->pitch;
+        p.up_row0 = h->peer_up_H + GHOST;
         p.wait_up = h->p2p_flags + 0;
         p.signal_up = h->peer_up_flags + 1;          // I am the upper neighbour's lower neighbour
     }
     if (has_down) {
         p.down_dst = h->peer_down_buf[b];
-        p.down_plane = (size_t)(h->peer_down_H + 2) * h->pitch;
+        p.down_plane = (size_t)(h->peer_down_H + 2 * GHOST) * h->pitch;
         p.wait_down = h->p2p_flags + 1;
         p.signal_down = h->peer_down_flags + 0;      // I am the lower neighbour's upper neighbour
     }
@@ -347,9 +400,11 @@ int enable_p2p(chemsim_lbm *h)
             if (t > 0.0) h->p2p_timeout_s = t;
         }
     }
-    const bool vec_ok = h->dtype == CHEMSIM_LBM_F32 ? face_p2p_supported(step_args<float>(h, 0, 1))
-                                                    : face_p2p_supported(step_args<double>(h, 0, 1));
-    if (!vec_ok) mine.ok = 0;                       // ragged widths keep the NCCL exchange
+    // the fused slab kernels need full 256-thread row chunks, >= 4 rows and the two-row halo;
+    // narrow, ragged or one-row slabs keep the NCCL exchange
+    const bool slab_ok = h->dtype == CHEMSIM_LBM_F32 ? slab_p2p_supported(step_args<float>(h, 0, h->H))
+                                                     : slab_p2p_supported(step_args<double>(h, 0, h->H));
+    if (!slab_ok || !deep_halo(h)) mine.ok = 0;
     if (mine.ok && (cudaIpcGetMemHandle(&mine.buf[0], h->buf[0]) != cudaSuccess ||
                     cudaIpcGetMemHandle(&mine.buf[1], h->buf[1]) != cudaSuccess ||
                     cudaIpcGetMemHandle(&mine.flags, h->p2p_flags) != cudaSuccess)) {
@@ -428,6 +483,10 @@ int begin_sharded(chemsim_lbm *h)
 {
     CUDA_TRY(h, cudaEventRecord(h->ev_interior, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_interior, 0));
+    if (deep_halo(h)) {
+        const int r = exchange_mask(h);
+        if (r) return r;
+    }
     if (!h->ghosts_valid) {
         if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
             // New populations (upload / restore) on every rank: restart the flag handshake from the
@@ -468,41 +527,58 @@ int step_impl(chemsim_lbm *h, int nsteps)
     }
     const int r0 = begin_sharded(h);
     if (r0) return r0;
-    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P && slab_p2p_supported(step_args<T>(h, 0, h->H))) {
-        // peer-memory mode, full-width rows: the whole step — face rows, halo stores into the
+    // Two steps per pass when every slab is at least two tiles tall (the same decision on every rank:
+    // it depends on the global shape only), an odd step on its own at the end.
+    const int TY = step2_tile_rows<T>();
+    const bool deep = deep_halo(h);
+    const bool can2 = deep && h->Hglobal / h->nranks >= 2 * TY && step2_supported(step_args<T>(h, 0, h->H));
+    int left = nsteps;
+    if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
+        // peer-memory mode: the whole step (or double step) — face rows, halo stores into the
         // neighbours' ghost rows, step flags, interior — is ONE kernel on the main stream
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_face, 0));   // the first exchange (begin_sharded)
-        for (int s = 0; s < nsteps; ++s) {
+        while (left > 0) {
+            const int n = (left >= 2 && can2) ? 2 : 1;
             StepArgs<T> all = step_args<T>(h, 0, h->H);
             fill_halo(h, all.halo);
-            LAUNCH_TRY(h, launch_slab_p2p<T>(all, h->stream));
+            if (n == 2) LAUNCH_TRY(h, launch_slab_p2p2<T>(all, h->stream));
+            else        LAUNCH_TRY(h, launch_slab_p2p<T>(all, h->stream));
             h->cur ^= 1;
-            h->step_index += 1;
+            h->step_index += n;
+            left -= n;
         }
         return 0;
     }
-    for (int s = 0; s < nsteps; ++s) {
-        // both waits refer to the events recorded for step s−1 (or by begin_sharded)
+    while (left > 0) {
+        const int n = (left >= 2 && can2) ? 2 : 1;
+        // both waits refer to the events recorded for the previous pass (or by begin_sharded)
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_face, 0));
         CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_interior, 0));
-        // halo stream: face rows {0, H−1} of step s, then ship them
-        StepArgs<T> face = step_args<T>(h, 0, h->H > 1 ? 2 : 1, h->H > 1 ? h->H - 1 : 1);
-        if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
-            // ONE kernel: face rows + stores into the neighbours' ghost rows + step flags
-            fill_halo(h, face.halo);
-            LAUNCH_TRY(h, launch_face_p2p<T>(face, h->comm_stream));
-            CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
-        } else {
-            LAUNCH_TRY(h, launch_step<T>(face, h->comm_stream));
+        // halo stream: the face rows of this pass, then ship them; main stream: the interior
+        if (n == 2) {
+            LAUNCH_TRY(h, launch_step2<T>(step_args<T>(h, 0, TY), h->comm_stream));
+            LAUNCH_TRY(h, launch_step2<T>(step_args<T>(h, h->H - TY, TY), h->comm_stream));
             CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
             const int r = exchange(h, h->cur ^ 1);
             if (r) return r;
+            if (h->H > 2 * TY) LAUNCH_TRY(h, launch_step2<T>(step_args<T>(h, TY, h->H - 2 * TY), h->stream));
+        } else {
+            const int face = deep ? 2 : 1;           // rows per face the neighbours receive
+            if (h->H <= 2 * face) {                  // every row is a face row
+                LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, h->H), h->comm_stream));
+            } else {
+                LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 0, face), h->comm_stream));
+                LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, h->H - face, face), h->comm_stream));
+            }
+            CUDA_TRY(h, cudaEventRecord(h->ev_face, h->comm_stream));
+            const int r = exchange(h, h->cur ^ 1);
+            if (r) return r;
+            if (h->H > 2 * face) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, face, h->H - 2 * face), h->stream));
         }
-        // main stream: interior of step s
-        if (h->H > 2) LAUNCH_TRY(h, launch_step<T>(step_args<T>(h, 1, h->H - 2), h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_interior, h->stream));
         h->cur ^= 1;
-        h->step_index += 1;
+        h->step_index += n;
+        left -= n;
     }
     // later work on the main stream (readouts, uploads) sees the finished halo work
     CUDA_TRY(h, cudaEventRecord(h->ev_halo, h->comm_stream));
@@ -682,7 +758,7 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
     h->esize = dtype == CHEMSIM_LBM_F32 ? 4 : 8;
     const int per_line = (int)(128 / h->esize);
     h->pitch = ((width + per_line - 1) / per_line) * per_line;
-    h->plane = (size_t)(h->H + 2) * h->pitch;
+    h->plane = (size_t)(h->H + 2 * GHOST) * h->pitch;
     h->mask_pitch = ((width + 127) / 128) * 128;
     h->flag_pitch = (((width + MASK_SEGMENT - 1) / MASK_SEGMENT + 2 + 15) / 16) * 16;
     rebuild_scalars(h);
@@ -710,8 +786,9 @@ int create_impl(int width, int global_height, int dtype, int edge, int device, i
         CREATE_TRY(cudaMalloc(&h->buf[b], buf_bytes));
         CREATE_TRY(cudaMemsetAsync(h->buf[b], 0, buf_bytes, h->stream));   // ghost rows of a zero-fill edge stay 0
     }
-    CREATE_TRY(cudaMalloc((void **)&h->mask, (size_t)h->H * h->mask_pitch));
-    CREATE_TRY(cudaMemsetAsync(h->mask, 0, (size_t)h->H * h->mask_pitch, h->stream));
+    CREATE_TRY(cudaMalloc((void **)&h->mask_alloc, (size_t)(h->H + 2) * h->mask_pitch));
+    CREATE_TRY(cudaMemsetAsync(h->mask_alloc, 0, (size_t)(h->H + 2) * h->mask_pitch, h->stream));
+    h->mask = h->mask_alloc + h->mask_pitch;
     CREATE_TRY(cudaMalloc((void **)&h->mask_flags, (size_t)h->H * h->flag_pitch));
     CREATE_TRY(cudaMemsetAsync(h->mask_flags, 0, (size_t)h->H * h->flag_pitch, h->stream));
     CREATE_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
@@ -795,10 +872,11 @@ int chemsim_lbm_slab_rows(int global_height, int rank, int nranks, int *row_offs
     return CHEMSIM_LBM_OK;
 }
 
-int chemsim_lbm_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out, int *count)
+int chemsim_lbm_halo_plan(int global_height, int rank, int nranks, int edge, chemsim_lbm_halo_msg *out, int *count)
 {
-    if (!out || !count || nranks < 1 || rank < 0 || rank >= nranks) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
-    *count = build_halo_plan(rank, nranks, edge, out);
+    if (!out || !count || nranks < 1 || rank < 0 || rank >= nranks || global_height < nranks)
+        return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    *count = build_halo_plan(global_height, rank, nranks, edge, out);
     return CHEMSIM_LBM_OK;
 }
 
@@ -868,7 +946,7 @@ int chemsim_lbm_destroy(chemsim_lbm_t *h)
     if (h->ev_mask) cudaEventDestroy(h->ev_mask);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
-    if (h->mask) cudaFree(h->mask);
+    if (h->mask_alloc) cudaFree(h->mask_alloc);
     if (h->mask_flags) cudaFree(h->mask_flags);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_scalar) cudaFree(h->d_scalar);

@@ -8,9 +8,9 @@
 // rounded operations, and the intermediate is held in the lattice dtype exactly as the A-B buffer
 // would hold it, so two passes of the single-step kernel and one pass of this one are bit-identical.
 //
-//   phase A  (TY+2) x (TX+2) cells ("ext" region): one cell per thread and iteration, scalar
-//            coalesced loads from HBM/L2; results go to smem[q][row][col + shift_q].  The rim is
-//            redundant work (+14 % cells for the 16 x 128 tile) whose loads hit L2 (the
+//   phase A  (TY+2) x (TX+2) cells ("ext" region): one cell per thread and iteration (two in
+//            flight), scalar coalesced loads from HBM/L2; results go to smem[q][row][col + shift_q].
+//            The rim is redundant work (+14 % cells for the 16 x 128 tile) whose loads hit L2 (the
 //            neighbouring tiles read the same lines).
 //   phase B  one warp per tile row, V = 16/sizeof(T) cells per lane: nine aligned 128-bit
 //            shared-memory loads (the per-population column shift_q makes every shifted read
@@ -18,7 +18,13 @@
 //
 // Edges: cells outside a zero-fill lattice hold 0 in the ext region (they are never computed:
 // src/lbm.rs:716-729 drops what leaves the array); periodic edges wrap the coordinates.  On a
-// y-slab the rows beyond the slab are the neighbours' cells, read from the TWO ghost rows.
+// y-slab the rows beyond the slab are the neighbours' cells: their populations come from the TWO
+// ghost rows, their solid flags from the mask's halo row (StepArgs::ghost_mask).
+//
+// step2_slab_p2p_kernel is the peer-memory form for a y-slab: the two FACE tile rows (rows
+// 0..TY-1 and H-TY..H-1) are dispatched first, wait for the neighbours' step flags, and store
+// rows 0, 1 / H-1, H-2 of the result straight into the neighbours' ghost rows before publishing
+// step t+2 (same protocol as step_slab_p2p_kernel).
 #pragma once
 
 #include "step_decl.cuh"
@@ -27,84 +33,89 @@ namespace chemsim {
 
 namespace {
 
-template <typename T>
-struct Step2Tile {
-    static constexpr int V = VecOf<T>::N;          // cells per 16 bytes
-    static constexpr int TX = 32 * V;              // one warp covers a tile row in phase B
-    static constexpr int TY = 16;
-    static constexpr int NT = 32 * TY;             // threads per block: one warp per tile row
-    static constexpr int EX = TX + 2, EY = TY + 2; // tile + one-cell rim
-    static constexpr int SP = ((EX + V - 1 + V - 1) / V) * V;   // shared row pitch (room for the column shift)
-    static constexpr size_t SMEM = (size_t)Q * EY * SP * sizeof(T);
-};
-
 // column shift of population q in shared memory: makes (x + 1 - ex_q + shift_q) a multiple of V
 template <int V> __host__ __device__ constexpr int shift_of(int q) { return (((ex_of(q) - 1) % V) + V) % V; }
 
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
-__global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
-step2_kernel(const __grid_constant__ StepArgs<T> a)
+// One tile: rows [ty0, ty0+TY) x columns [tx0, tx0+TX); rows >= y_end are not stored (tile rows
+// that overlap the next region).  P2P: also deliver the face rows to the neighbours.
+template <typename T, bool PERIODIC_X, int COL, bool P2P>
+__device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, const int tx0, const int ty0,
+                                           const int y_end, const int tok)
 {
     using TL = Step2Tile<T>;
     constexpr int V = TL::V, TX = TL::TX, TY = TL::TY, NT = TL::NT, EX = TL::EX, EY = TL::EY, SP = TL::SP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *const sm = reinterpret_cast<T *>(smem_raw);   // [Q][EY][SP]
-
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int tx0 = blockIdx.x * TX;
-    const int ty0 = a.y_begin + (blockIdx.z * gridDim.y + blockIdx.y) * TY;
-    if (ty0 >= a.y_begin + a.y_count) return;
-    const int y_end = a.y_begin + a.y_count;         // this launch owns tile rows [y_begin, y_end)
     const int tid = threadIdx.x;
-    const int tok = order_after_grid_dependency();
     const T *src = a.src + tok;
     const uint8_t *mask = a.mask + tok;
+    // does any cell this tile touches need the mask?  own rows: if the slab has solids; ghost rows
+    // (tiles at a slab face): the neighbour may have solids there even if this slab has none
+    const bool touches_ghost = ty0 == 0 || ty0 + TY >= a.H;
+    const bool use_mask = a.has_mask != 0 || (a.ghost_mask != 0 && touches_ghost);
 
     // ---- phase A: step n+1 on the ext region -> shared memory -----------------------------------
-    // interior tile: every source cell of the ext region lies inside this lattice (no wrap, no
-    // zero-fill, no ghost row of a zero-fill edge): block-uniform fast path
+    // interior tile: every source cell of the ext region lies inside this slab (no wrap, no
+    // zero-fill, no ghost row): block-uniform fast path
     const bool interior = ty0 >= 2 && ty0 + TY + 2 <= a.H && tx0 >= 2 && tx0 + TX + 2 <= a.W;
     if (interior) {
-        // two ext cells per iteration, all eighteen loads issued before the first collision: the
-        // HBM/L2 latency of one cell is covered by the arithmetic of the other
         constexpr int DY = NT / EX, DX = NT % EX;    // idx += NT  <=>  (ey, ex) += (DY, DX) with a carry
         int ey0 = tid / EX, ex0 = tid - ey0 * EX;
         // opaque base: keeps "pointer + precomputed offset" as two integer instructions per load
         unsigned long long base = reinterpret_cast<unsigned long long>(src) +
-                                  ((size_t)(ty0 - 1 + a.ghost) * a.pitch + (tx0 - 1)) * sizeof(T);
+                                  ((size_t)(ty0 - 1 + GHOST) * a.pitch + (tx0 - 1)) * sizeof(T);
         asm volatile("" : "+l"(base));
+        if constexpr (sizeof(T) == 4) {
+            // f32: two ext cells per iteration, all eighteen loads issued before the first collision —
+            // the HBM/L2 latency of one cell is covered by the arithmetic of the other
 #pragma unroll 1
-        for (int idx = tid; idx < EY * EX; idx += 2 * NT) {
-            int ey1 = ey0 + DY, ex1 = ex0 + DX;
-            if (ex1 >= EX) { ex1 -= EX; ey1 += 1; }
-            const bool two = idx + NT < EY * EX;
-            const char *p0 = reinterpret_cast<const char *>(base) + ((size_t)ey0 * a.pitch + ex0) * sizeof(T);
-            const char *p1 = reinterpret_cast<const char *>(base) + ((size_t)(two ? ey1 : ey0) * a.pitch + (two ? ex1 : ex0)) * sizeof(T);
-            T c0[Q], c1[Q];
+            for (int idx = tid; idx < EY * EX; idx += 2 * NT) {
+                int ey1 = ey0 + DY, ex1 = ex0 + DX;
+                if (ex1 >= EX) { ex1 -= EX; ey1 += 1; }
+                const bool two = idx + NT < EY * EX;
+                if (!two) { ey1 = ey0; ex1 = ex0; }  // no second cell: re-read the first (result discarded)
+                const char *p0 = reinterpret_cast<const char *>(base) + ((size_t)ey0 * a.pitch + ex0) * sizeof(T);
+                const char *p1 = reinterpret_cast<const char *>(base) + ((size_t)ey1 * a.pitch + ex1) * sizeof(T);
+                T c0[Q], c1[Q];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                c0[q] = __ldg(reinterpret_cast<const T *>(p0 + (a.ld_off[q] - ex_of(q) * (long long)sizeof(T))));
-                c1[q] = __ldg(reinterpret_cast<const T *>(p1 + (a.ld_off[q] - ex_of(q) * (long long)sizeof(T))));
-            }
-            bool s0 = false, s1 = false;
-            if (HAS_MASK) {
-                s0 = __ldg(mask + (size_t)(ty0 - 1 + ey0) * a.mask_pitch + (tx0 - 1 + ex0)) != 0;
-                s1 = __ldg(mask + (size_t)(ty0 - 1 + (two ? ey1 : ey0)) * a.mask_pitch + (tx0 - 1 + (two ? ex1 : ex0))) != 0;
-            }
-            if (HAS_MASK) bounce_back(c0, s0);
-            collide<COL>(c0, a.k);
-            T *d0 = sm + ey0 * SP + ex0;
+                for (int q = 0; q < Q; ++q) {
+                    c0[q] = __ldg(reinterpret_cast<const T *>(p0 + (a.ld_off[q] - ex_of(q) * (long long)sizeof(T))));
+                    c1[q] = __ldg(reinterpret_cast<const T *>(p1 + (a.ld_off[q] - ex_of(q) * (long long)sizeof(T))));
+                }
+                if (use_mask) {
+                    const bool s0 = __ldg(mask + (size_t)(ty0 - 1 + ey0) * a.mask_pitch + (tx0 - 1 + ex0)) != 0;
+                    const bool s1 = __ldg(mask + (size_t)(ty0 - 1 + ey1) * a.mask_pitch + (tx0 - 1 + ex1)) != 0;
+                    bounce_back(c0, s0);
+                    bounce_back(c1, s1);
+                }
+                collide<COL>(c0, a.k);
+                T *d0 = sm + ey0 * SP + ex0;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) d0[q * (EY * SP) + shift_of<V>(q)] = c0[q];
-            if (two) {
-                if (HAS_MASK) bounce_back(c1, s1);
-                collide<COL>(c1, a.k);
-                T *d1 = sm + ey1 * SP + ex1;
+                for (int q = 0; q < Q; ++q) d0[q * (EY * SP) + shift_of<V>(q)] = c0[q];
+                if (two) {
+                    collide<COL>(c1, a.k);
+                    T *d1 = sm + ey1 * SP + ex1;
 #pragma unroll
-                for (int q = 0; q < Q; ++q) d1[q * (EY * SP) + shift_of<V>(q)] = c1[q];
+                    for (int q = 0; q < Q; ++q) d1[q * (EY * SP) + shift_of<V>(q)] = c1[q];
+                }
+                ey0 = ey1 + DY; ex0 = ex1 + DX;
+                if (ex0 >= EX) { ex0 -= EX; ey0 += 1; }
             }
-            ey0 = ey1 + DY; ex0 = ex1 + DX;
-            if (ex0 >= EX) { ex0 -= EX; ey0 += 1; }
+        } else {
+            // f64: one cell per iteration (two would spill at 64 registers)
+#pragma unroll 1
+            for (int idx = tid; idx < EY * EX; idx += NT) {
+                const char *p0 = reinterpret_cast<const char *>(base) + ((size_t)ey0 * a.pitch + ex0) * sizeof(T);
+                T c0[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    c0[q] = __ldg(reinterpret_cast<const T *>(p0 + (a.ld_off[q] - ex_of(q) * (long long)sizeof(T))));
+                if (use_mask) bounce_back(c0, __ldg(mask + (size_t)(ty0 - 1 + ey0) * a.mask_pitch + (tx0 - 1 + ex0)) != 0);
+                collide<COL>(c0, a.k);
+                T *d0 = sm + ey0 * SP + ex0;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) d0[q * (EY * SP) + shift_of<V>(q)] = c0[q];
+                ey0 += DY; ex0 += DX;
+                if (ex0 >= EX) { ex0 -= EX; ey0 += 1; }
+            }
         }
     } else {
 #pragma unroll 1
@@ -130,11 +141,13 @@ step2_kernel(const __grid_constant__ StepArgs<T> a)
                     if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
                     if (PERIODIC_X) { if (sx < 0) sx = a.W - 1; else if (sx >= a.W) sx = 0; }
                     else            in = sx >= 0 && sx < a.W;
-                    // rows -ghost .. H+ghost-1 exist: ghost rows hold the neighbour slab's cells, or 0 at a zero-fill edge
-                    c[q] = in ? __ldg(src + (size_t)q * a.plane + (size_t)(sy + a.ghost) * a.pitch + sx) : T(0);
+                    // rows -GHOST .. H+GHOST-1 exist: ghost rows hold the neighbour slab's cells, or 0 at a zero-fill edge
+                    const T *cell = src + (size_t)q * a.plane + (size_t)(sy + GHOST) * a.pitch + sx;
+                    // ghost rows are written by the neighbouring GPU while this kernel may be resident: coherent load
+                    c[q] = in ? (P2P ? *reinterpret_cast<const volatile T *>(cell) : __ldg(cell)) : T(0);
                 }
-                // the mask of a ghost-row cell belongs to the neighbour slab: a.mask has `ghost` halo rows too
-                if (HAS_MASK) bounce_back(c, __ldg(mask + (ptrdiff_t)gy * a.mask_pitch + gx) != 0);
+                // gy may be -1 or H on a slab: the mask's halo row holds the neighbour's face row
+                if (use_mask) bounce_back(c, mask[(ptrdiff_t)gy * a.mask_pitch + gx] != 0);
                 collide<COL>(c, a.k);
             }
             T *s = sm + ey * SP + ex;
@@ -158,20 +171,70 @@ step2_kernel(const __grid_constant__ StepArgs<T> a)
         else                  { g[q][0] = v.x; g[q][1] = v.y; }
     }
     unsigned maskw = 0;
-    if (HAS_MASK) maskw = ldg_mask(mask + (size_t)gy * a.mask_pitch + gx0, true, (const T *)nullptr);
+    if (use_mask) maskw = ldg_mask(mask + (size_t)gy * a.mask_pitch + gx0, true, (const T *)nullptr);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         T c[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) c[q] = g[q][j];
-        if (HAS_MASK) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
+        if (use_mask) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
         collide<COL>(c, a.k);
 #pragma unroll
         for (int q = 0; q < Q; ++q) g[q][j] = c[q];
     }
-    char *out = reinterpret_cast<char *>(a.dst) + ((size_t)(gy + a.ghost) * a.pitch + gx0) * sizeof(T);
+    char *out = reinterpret_cast<char *>(a.dst) + ((size_t)(gy + GHOST) * a.pitch + gx0) * sizeof(T);
 #pragma unroll
     for (int q = 0; q < Q; ++q) store_vec(reinterpret_cast<T *>(out + a.st_off[q]), g[q]);
+    if (P2P) halo_store_row(a, gy, gx0, g);
+}
+
+// rows [y_begin, y_begin + y_count) advance by two steps (unsharded lattice, or one region of a slab)
+template <typename T, bool PERIODIC_X, int COL>
+__global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
+step2_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    using TL = Step2Tile<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int y_end = a.y_begin + a.y_count;
+    const int ty0 = a.y_begin + (blockIdx.z * gridDim.y + blockIdx.y) * TL::TY;
+    if (ty0 >= y_end) return;
+    step2_tile<T, PERIODIC_X, COL, false>(a, reinterpret_cast<T *>(smem_raw), blockIdx.x * TL::TX, ty0, y_end,
+                                          order_after_grid_dependency());
+}
+
+// a whole y-slab, H >= 2 TY: tile-row slot 0 -> rows [0, TY), slot 1 -> rows [H-TY, H) (the two face
+// tile rows, dispatched first), slot s >= 2 -> rows [(s-1) TY, ...) clipped at H-TY
+template <typename T, bool PERIODIC_X, int COL>
+__global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
+step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
+{
+    using TL = Step2Tile<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;");
+    T *const sm = reinterpret_cast<T *>(smem_raw);
+    const int slot = blockIdx.z * gridDim.y + blockIdx.y;
+    const int tx0 = blockIdx.x * TL::TX;
+    if (slot >= 2) {                                 // interior tile row: no ghost row, feeds no neighbour
+        const int ty0 = (slot - 1) * TL::TY;
+        if (ty0 >= a.H - TL::TY) return;
+        step2_tile<T, PERIODIC_X, COL, false>(a, sm, tx0, ty0, a.H - TL::TY, order_after_grid_dependency());
+        return;
+    }
+    const HaloP2P &p = a.halo;
+    const int ty0 = slot == 0 ? 0 : a.H - TL::TY;
+    const int tok = order_after_grid_dependency() + order_after_halo_flags(p, slot == 0, slot == 1);
+    step2_tile<T, PERIODIC_X, COL, true>(a, sm, tx0, ty0, ty0 + TL::TY, tok);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) publish_step(p, 2u * gridDim.x, 2u);
+}
+
+template <typename K>
+void step2_opt_in(K kernel, size_t smem)
+{
+    // > 48 KB of dynamic shared memory needs an opt-in per function and device
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 }  // namespace
@@ -183,24 +246,30 @@ void launch_step2_col(const StepArgs<T> &a, cudaStream_t s)
     using TL = Step2Tile<T>;
     const dim3 block(TL::NT);
     const dim3 grid = row_grid((a.W + TL::TX - 1) / TL::TX, (a.y_count + TL::TY - 1) / TL::TY);
-#define CHEMSIM_LAUNCH_STEP2(PX, HM)                                                                           \
-    do {                                                                                                       \
-        static bool opted_in_[64] = {};            /* per device: > 48 KB of dynamic shared memory */          \
-        int dev_ = 0;                                                                                          \
-        cudaGetDevice(&dev_);                                                                                  \
-        if (!opted_in_[dev_ & 63]) {                                                                           \
-            cudaFuncSetAttribute(step2_kernel<T, PX, HM, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                 (int)TL::SMEM);                                                               \
-            opted_in_[dev_ & 63] = true;                                                                       \
-        }                                                                                                      \
-        launch_chained(step2_kernel<T, PX, HM, COL>, grid, block, s, a, TL::SMEM);                             \
-    } while (0)
     if (a.periodic_x) {
-        if (a.has_mask) CHEMSIM_LAUNCH_STEP2(true, true); else CHEMSIM_LAUNCH_STEP2(true, false);
+        step2_opt_in(step2_kernel<T, true, COL>, TL::SMEM);
+        launch_chained(step2_kernel<T, true, COL>, grid, block, s, a, TL::SMEM);
     } else {
-        if (a.has_mask) CHEMSIM_LAUNCH_STEP2(false, true); else CHEMSIM_LAUNCH_STEP2(false, false);
+        step2_opt_in(step2_kernel<T, false, COL>, TL::SMEM);
+        launch_chained(step2_kernel<T, false, COL>, grid, block, s, a, TL::SMEM);
     }
-#undef CHEMSIM_LAUNCH_STEP2
+}
+
+// the whole slab, two steps, with the peer-memory halo (H >= 2 TY)
+template <typename T, int COL>
+void launch_slab_p2p2_col(const StepArgs<T> &a, cudaStream_t s)
+{
+    using TL = Step2Tile<T>;
+    const dim3 block(TL::NT);
+    const int interior_rows = a.H - 2 * TL::TY;
+    const dim3 grid = row_grid((a.W + TL::TX - 1) / TL::TX, 2 + (interior_rows + TL::TY - 1) / TL::TY);
+    if (a.periodic_x) {
+        step2_opt_in(step2_slab_p2p_kernel<T, true, COL>, TL::SMEM);
+        launch_chained(step2_slab_p2p_kernel<T, true, COL>, grid, block, s, a, TL::SMEM);
+    } else {
+        step2_opt_in(step2_slab_p2p_kernel<T, false, COL>, TL::SMEM);
+        launch_chained(step2_slab_p2p_kernel<T, false, COL>, grid, block, s, a, TL::SMEM);
+    }
 }
 
 }  // namespace chemsim

@@ -4,4 +4,5 @@
 
 namespace chemsim {
 CHEMSIM_INSTANTIATE_STEP(COL_BGK)
+CHEMSIM_INSTANTIATE_STEP2(COL_BGK)
 }  // namespace chemsim

@@ -29,7 +29,19 @@ inline bool use_vec(const StepArgs<T> &a) { return a.W % VecOf<T>::N == 0; }
 // rows [y_begin, ...) of a lattice / the whole slab incl. the peer-memory halo / the two face rows.
 template <typename T, int COL> void launch_step_col(const StepArgs<T> &a, cudaStream_t s);
 template <typename T, int COL> void launch_slab_p2p_col(const StepArgs<T> &a, cudaStream_t s);
-template <typename T, int COL> void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s);
 template <typename T, int COL> void launch_step2_col(const StepArgs<T> &a, cudaStream_t s);
+template <typename T, int COL> void launch_slab_p2p2_col(const StepArgs<T> &a, cudaStream_t s);
+
+// tile of the two-steps-per-pass kernel (step2_impl.cuh)
+template <typename T>
+struct Step2Tile {
+    static constexpr int V = VecOf<T>::N;          // cells per 16 bytes
+    static constexpr int TX = 32 * V;              // one warp covers a tile row in phase B
+    static constexpr int TY = 16;
+    static constexpr int NT = 32 * TY;             // threads per block: one warp per tile row
+    static constexpr int EX = TX + 2, EY = TY + 2; // tile + one-cell rim
+    static constexpr int SP = ((EX + V - 1 + V - 1) / V) * V;   // shared row pitch (room for the column shift)
+    static constexpr size_t SMEM = (size_t)Q * EY * SP * sizeof(T);
+};
 
 }  // namespace chemsim

@@ -135,6 +135,28 @@ __device__ __forceinline__ int order_after_grid_dependency()
     return tok;
 }
 
+// Peer-memory halo: the V cells at (y, x0..) of all nine populations, just computed, go where the
+// neighbouring GPU's next pass reads them (see HaloP2P): rows 0/1 to the upper neighbour's ghost
+// rows H_up/H_up+1, rows H-1/H-2 to the lower neighbour's ghost rows -1/-2; the outer row of
+// each pair only needs the populations that move towards the face.
+template <typename T, int V>
+__device__ __forceinline__ void halo_store_row(const StepArgs<T> &a, int y, int x0, const T (&g)[Q][V])
+{
+    const HaloP2P &p = a.halo;
+    if (p.up_dst && y <= 1) {
+        T *peer = (T *)p.up_dst + (size_t)(p.up_row0 + y) * a.pitch + x0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            if (y == 0 || ey_of(q) == -1) store_vec(peer + (size_t)q * p.up_plane, g[q]);
+    }
+    if (p.down_dst && y >= a.H - 2) {
+        T *peer = (T *)p.down_dst + (size_t)(GHOST - (a.H - y)) * a.pitch + x0;    // row H-1 -> GHOST-1, H-2 -> GHOST-2
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            if (y == a.H - 1 || ey_of(q) == 1) store_vec(peer + (size_t)q * p.down_plane, g[q]);
+    }
+}
+
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool P2P>
 __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y, const int xv, const int lane,
                                               const int halo_tok)
@@ -168,7 +190,7 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     // (a.ld_off[q] = (q*plane - ey_q*pitch)*sizeof(T), a kernel-parameter constant that SASS
     // uses as an immediate operand), so a load costs two integer instructions.  Rows 0 / H-1 of an
     // unsharded periodic lattice shift the base by +-H rows (block-uniform) instead of reading ghosts.
-    const char *p0 = reinterpret_cast<const char *>(src) + ((size_t)(y + 1) * a.pitch + x0) * sizeof(T);
+    const char *p0 = reinterpret_cast<const char *>(src) + ((size_t)(y + GHOST) * a.pitch + x0) * sizeof(T);
     const char *pu = p0, *pd = p0;                   // bases of the dy = +1 / dy = -1 movers' source rows
     if (a.wrap_y) { if (y == 0) pu = p0 + a.wrap_bytes; if (y == a.H - 1) pd = p0 - a.wrap_bytes; }
     // left / right edge element relative to the vector: x0-1 (wrapped: W-1, and first => x0 == 0) / x0+V (wrapped: 0)
@@ -223,24 +245,12 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     }
 
     // ---- phase 4: nine aligned vector stores ------------------------------------
-    char *out = reinterpret_cast<char *>(a.dst) + ((size_t)(y + 1) * a.pitch + x0) * sizeof(T);
+    char *out = reinterpret_cast<char *>(a.dst) + ((size_t)(y + GHOST) * a.pitch + x0) * sizeof(T);
 #pragma unroll
     for (int q = 0; q < Q; ++q) store_vec(reinterpret_cast<T *>(out + a.st_off[q]), g[q]);
 
     // ---- phase 5 (P2P face rows): the halo, written where the neighbour reads it --
-    if (P2P) {
-        const HaloP2P &p = a.halo;
-        if (y == a.H - 1 && p.down_dst) {            // dy=+1 movers -> lower neighbour's ghost row −1 (plane row 0)
-            T *peer = (T *)p.down_dst + x0;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) if (ey_of(q) == 1) store_vec(peer + (size_t)q * p.down_plane, g[q]);
-        }
-        if (y == 0 && p.up_dst) {                    // dy=−1 movers -> upper neighbour's ghost row H_up
-            T *peer = (T *)p.up_dst + (size_t)p.up_ghost_row * a.pitch + x0;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) if (ey_of(q) == -1) store_vec(peer + (size_t)q * p.up_plane, g[q]);
-        }
-    }
+    if (P2P) halo_store_row(a, y, x0, g);
 }
 
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL, bool MULTIROW>
@@ -308,12 +318,12 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned want, c
 
 // One thread waits for both neighbours' step flags, the block follows through a barrier.
 // Returns 0 through shared memory: an order token for the ghost-row loads (see ldg_*).
-__device__ __forceinline__ int order_after_halo_flags(const HaloP2P &p)
+__device__ __forceinline__ int order_after_halo_flags(const HaloP2P &p, bool need_up = true, bool need_down = true)
 {
     __shared__ int token;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        wait_flag(p.wait_up, p.step, p);
-        wait_flag(p.wait_down, p.step, p);
+        if (need_up) wait_flag(p.wait_up, p.step, p);
+        if (need_down) wait_flag(p.wait_down, p.step, p);
         token = 0;
     }
     __syncthreads();
@@ -323,32 +333,15 @@ __device__ __forceinline__ int order_after_halo_flags(const HaloP2P &p)
 // The last face block to finish publishes step t+1 into both neighbours' flags — unless a wait
 // timed out (now or in an earlier step): a poisoned lattice never tells its neighbours to go on,
 // so they time out as well instead of consuming a stale halo.
-__device__ __forceinline__ void publish_step(const HaloP2P &p, unsigned total_face_blocks)
+__device__ __forceinline__ void publish_step(const HaloP2P &p, unsigned total_face_blocks, unsigned steps = 1)
 {
     if (atomicAdd(p.done, 1u) == total_face_blocks - 1) {
         *p.done = 0;
         __threadfence_system();
         if (*reinterpret_cast<volatile int *>(p.error) != 0) return;
-        if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + 1;
-        if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + 1;
+        if (p.signal_down) *reinterpret_cast<volatile unsigned *>(p.signal_down) = p.step + steps;
+        if (p.signal_up)   *reinterpret_cast<volatile unsigned *>(p.signal_up) = p.step + steps;
     }
-}
-
-template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
-__global__ void __launch_bounds__(STEP_THREADS, 1)
-step_face_p2p_kernel(const __grid_constant__ StepArgs<T> a)
-{
-    const HaloP2P &p = a.halo;
-    const int halo_tok = order_after_halo_flags(p);
-    const int yi = blockIdx.x * blockDim.y + threadIdx.y;
-    if (yi < a.y_count)
-        step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, a.y_begin + yi * a.y_stride,
-                                                          blockIdx.y * blockDim.x + threadIdx.x, threadIdx.x & 31,
-                                                          halo_tok);
-    __threadfence_system();                          // my stores (local and peer) are visible system-wide ...
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0)
-        publish_step(p, gridDim.x * gridDim.y);      // ... before the last block publishes the step
 }
 
 // ---- the fused step, one cell per thread (any width) -------------------------
@@ -369,12 +362,12 @@ step_scalar_kernel(const __grid_constant__ StepArgs<T> a)
         bool inside = true;
         if (sx < 0)         { if (a.periodic_x) sx = a.W - 1; else inside = false; }
         else if (sx >= a.W) { if (a.periodic_x) sx = 0;       else inside = false; }
-        c[q] = inside ? a.src[(size_t)q * a.plane + (size_t)(sy + 1) * a.pitch + sx] : T(0);
+        c[q] = inside ? a.src[(size_t)q * a.plane + (size_t)(sy + GHOST) * a.pitch + sx] : T(0);
     }
     if (a.has_mask) bounce_back(c, a.mask[(size_t)y * a.mask_pitch + x] != 0);
     collide<COL>(c, a.k);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) a.dst[(size_t)q * a.plane + (size_t)(y + 1) * a.pitch + x] = c[q];
+    for (int q = 0; q < Q; ++q) a.dst[(size_t)q * a.plane + (size_t)(y + GHOST) * a.pitch + x] = c[q];
 }
 
 }  // namespace
@@ -448,12 +441,12 @@ void launch_step_col(const StepArgs<T> &a_in, cudaStream_t s)
 namespace {
 
 // ---- the whole slab step + halo in ONE kernel (peer-memory mode) ------------------
-// Grid of x-chunks (fastest) x H row slots; row slot r = 0 -> row 0, 1 -> row H−1,
-// r >= 2 -> row r−1, so the two face rows are dispatched first: they wait for the neighbours' step flags, update
-// their rows, store the outgoing populations into the neighbours' ghost rows and publish
-// the next step early, while the remaining blocks stream through the interior.  One
-// launch per step and GPU, chained with programmatic dependent launch; no events, no
-// communication kernel, no second stream.
+// Grid of x-chunks (fastest) x H row slots.  The four face rows come first (slots 0..3 -> rows
+// 0, 1, H-1, H-2): they wait for the neighbours' step flags (row 0 / H-1 read a ghost row), update
+// their rows, store them into the neighbours' ghost rows and publish the next step early, while
+// the remaining blocks stream through the interior.  One launch per step and GPU, chained with
+// programmatic dependent launch; no events, no communication kernel, no second stream.
+// Needs H >= 4 (slab_p2p_supported).
 template <typename T, bool PERIODIC_X, bool HAS_MASK, int COL>
 __global__ void __launch_bounds__(STEP_THREADS, step_min_blocks<T, COL>())
 step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
@@ -461,18 +454,18 @@ step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     asm volatile("griddepcontrol.launch_dependents;");
     const int r = blockIdx.z * gridDim.y + blockIdx.y, xc = blockIdx.x;
     if (r >= a.H) return;                            // padding of the row dimension (block-uniform)
-    const int y = r == 0 ? 0 : (r == 1 ? a.H - 1 : r - 1);
+    const int y = r == 0 ? 0 : (r == 1 ? 1 : (r == 2 ? a.H - 1 : (r == 3 ? a.H - 2 : r - 2)));
     const int xv = xc * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if (r >= 2) {                                    // interior row: reads no ghost row
+    if (r >= 4) {                                    // interior row: reads no ghost row, feeds no neighbour
         step_vec_body<T, PERIODIC_X, HAS_MASK, COL, false>(a, y, xv, lane, 0);
         return;
     }
     const HaloP2P &p = a.halo;
-    const int halo_tok = order_after_halo_flags(p);
+    const int halo_tok = order_after_halo_flags(p, r == 0, r == 2);    // rows 1 and H-2 read no ghost row
     step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane, halo_tok);
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) publish_step(p, (a.H > 1 ? 2u : 1u) * (unsigned)a.xchunks);
+    if (threadIdx.x == 0) publish_step(p, 4u * (unsigned)a.xchunks);
 }
 
 }  // namespace
@@ -495,40 +488,23 @@ void launch_slab_p2p_col(const StepArgs<T> &a_in, cudaStream_t s)
     }
 }
 
-template <typename T, int COL>
-void launch_face_p2p_col(const StepArgs<T> &a, cudaStream_t s)
-{
-    constexpr int V = VecOf<T>::N;
-    const int rows = a.y_count, nvec = a.W / V;
-    int bx = ((nvec + 31) / 32) * 32;
-    if (bx > STEP_THREADS) bx = STEP_THREADS;
-    int by = STEP_THREADS / bx;
-    if (by > rows) by = rows;
-    const dim3 block(bx, by);
-    const dim3 grid((rows + by - 1) / by, (nvec + bx - 1) / bx);
-    if (a.periodic_x) {
-        if (a.has_mask) step_face_p2p_kernel<T, true, true, COL><<<grid, block, 0, s>>>(a);
-        else            step_face_p2p_kernel<T, true, false, COL><<<grid, block, 0, s>>>(a);
-    } else {
-        if (a.has_mask) step_face_p2p_kernel<T, false, true, COL><<<grid, block, 0, s>>>(a);
-        else            step_face_p2p_kernel<T, false, false, COL><<<grid, block, 0, s>>>(a);
-    }
-}
-
 }  // namespace chemsim
 
 #include "step2_impl.cuh"
 
 namespace chemsim {
 
-#define CHEMSIM_INSTANTIATE_STEP(COL)                                                              \
+// the two-step kernels (not for KBC: compute-bound, the redundant rim makes it slower than two single steps)
+#define CHEMSIM_INSTANTIATE_STEP2(COL)                                                             \
     template void launch_step2_col<float, COL>(const StepArgs<float> &, cudaStream_t);             \
     template void launch_step2_col<double, COL>(const StepArgs<double> &, cudaStream_t);           \
+    template void launch_slab_p2p2_col<float, COL>(const StepArgs<float> &, cudaStream_t);         \
+    template void launch_slab_p2p2_col<double, COL>(const StepArgs<double> &, cudaStream_t);
+
+#define CHEMSIM_INSTANTIATE_STEP(COL)                                                              \
     template void launch_step_col<float, COL>(const StepArgs<float> &, cudaStream_t);              \
     template void launch_step_col<double, COL>(const StepArgs<double> &, cudaStream_t);            \
     template void launch_slab_p2p_col<float, COL>(const StepArgs<float> &, cudaStream_t);          \
-    template void launch_slab_p2p_col<double, COL>(const StepArgs<double> &, cudaStream_t);        \
-    template void launch_face_p2p_col<float, COL>(const StepArgs<float> &, cudaStream_t);          \
-    template void launch_face_p2p_col<double, COL>(const StepArgs<double> &, cudaStream_t);
+    template void launch_slab_p2p_col<double, COL>(const StepArgs<double> &, cudaStream_t);
 
 }  // namespace chemsim

@@ -4,4 +4,5 @@
 
 namespace chemsim {
 CHEMSIM_INSTANTIATE_STEP(COL_REGULARIZED)
+CHEMSIM_INSTANTIATE_STEP2(COL_REGULARIZED)
 }  // namespace chemsim

@@ -4,4 +4,5 @@
 
 namespace chemsim {
 CHEMSIM_INSTANTIATE_STEP(COL_TRT)
+CHEMSIM_INSTANTIATE_STEP2(COL_TRT)
 }  // namespace chemsim

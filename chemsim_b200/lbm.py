@@ -521,12 +521,12 @@ def slab_rows(global_height: int, rank: int, nranks: int):
     return r0.value, rows.value
 
 
-def halo_plan(rank: int, nranks: int, edge: int):
-    """The per-step halo messages of one rank, in issue order (host-only):
+def halo_plan(global_height: int, rank: int, nranks: int, edge: int):
+    """The halo messages of one rank per exchange, in issue order (host-only):
     list of (is_send, peer, q, row) with row one of _ffi.ROW_*."""
     buf = (_ffi.HaloMsg * _ffi.HALO_PLAN_MAX)()
     n = C.c_int()
-    _ffi.check(_ffi.load().chemsim_lbm_halo_plan(rank, nranks, edge, buf, C.byref(n)), None)
+    _ffi.check(_ffi.load().chemsim_lbm_halo_plan(global_height, rank, nranks, edge, buf, C.byref(n)), None)
     return [(bool(m.is_send), m.peer, m.q, m.row) for m in buf[: n.value]]
 
 

@@ -111,13 +111,21 @@ int chemsim_lbm_halo_mode(const chemsim_lbm_t *h, int *mode);
 
 /* Host-only helpers that expose the sharding logic (no GPU needed; the CPU tests
  * drive a gloo emulation of the exchange with them).
- * slab_rows: the rows rank `rank` owns.  halo_plan: the messages one rank issues
- * per step, in issue order; `out` must hold CHEMSIM_LBM_HALO_PLAN_MAX entries. */
+ * slab_rows: the rows rank `rank` owns.  halo_plan: the messages one rank issues per
+ * exchange, in issue order; `out` must hold CHEMSIM_LBM_HALO_PLAN_MAX entries.  A slab
+ * keeps TWO ghost rows per side, because one pass may advance the lattice by two steps:
+ * per face it sends its outermost row (all nine populations) and, of the next row, the
+ * three populations that move towards the face.  If some slab has a single row
+ * (global_height / nranks < 2) the plan is the one-row form: three populations per face. */
 typedef enum {
-    CHEMSIM_LBM_ROW_FIRST = 0,       /* local row 0            (send) */
-    CHEMSIM_LBM_ROW_LAST = 1,        /* local row H-1          (send) */
-    CHEMSIM_LBM_ROW_GHOST_ABOVE = 2, /* ghost row -1           (recv) */
-    CHEMSIM_LBM_ROW_GHOST_BELOW = 3  /* ghost row H            (recv) */
+    CHEMSIM_LBM_ROW_FIRST = 0,        /* local row 0            (send) */
+    CHEMSIM_LBM_ROW_LAST = 1,         /* local row H-1          (send) */
+    CHEMSIM_LBM_ROW_GHOST_ABOVE = 2,  /* ghost row -1           (recv) */
+    CHEMSIM_LBM_ROW_GHOST_BELOW = 3,  /* ghost row H            (recv) */
+    CHEMSIM_LBM_ROW_SECOND = 4,       /* local row 1            (send) */
+    CHEMSIM_LBM_ROW_SECOND_LAST = 5,  /* local row H-2          (send) */
+    CHEMSIM_LBM_ROW_GHOST_ABOVE2 = 6, /* ghost row -2           (recv) */
+    CHEMSIM_LBM_ROW_GHOST_BELOW2 = 7  /* ghost row H+1          (recv) */
 } chemsim_lbm_halo_row;
 typedef struct {
     int is_send; /* 1 = ncclSend, 0 = ncclRecv */
@@ -125,9 +133,10 @@ typedef struct {
     int q;       /* population index 0..8 */
     int row;     /* chemsim_lbm_halo_row */
 } chemsim_lbm_halo_msg;
-#define CHEMSIM_LBM_HALO_PLAN_MAX 12
+#define CHEMSIM_LBM_HALO_PLAN_MAX 48
 int chemsim_lbm_slab_rows(int global_height, int rank, int nranks, int *row_offset, int *rows);
-int chemsim_lbm_halo_plan(int rank, int nranks, int edge, chemsim_lbm_halo_msg *out, int *count);
+int chemsim_lbm_halo_plan(int global_height, int rank, int nranks, int edge, chemsim_lbm_halo_msg *out,
+                          int *count);
 
 /* Device-side barrier over the ranks of a sharded lattice: a one-element ncclAllReduce queued on
  * the handle's stream (asynchronous for the host).  Work queued after it starts on every rank at

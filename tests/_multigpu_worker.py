@@ -54,7 +54,7 @@ def main():
     # f-3 / f-4 on a sharded lattice: every rank paints the same GLOBAL rectangle (it straddles a
     # slab face: rows around hg/2 and around the lattice's first rows), checkpoints, steps, restores
     # and replays; rank 0 compares with the oracle run on the host-edited mask.
-    ry, rh = max(0, hg // 2 - 3), min(7, hg)
+    ry, rh = max(0, hg // 2 - 3), min(7, hg - max(0, hg // 2 - 3))
     state.paint_rect(w // 4, ry, max(1, w // 2), rh, True)
     state.paint_rect(-3, -2, 9, 4, True)
     state.step(2)

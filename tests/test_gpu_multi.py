@@ -16,10 +16,11 @@ def n_gpus():
     return torch.cuda.device_count()
 
 
-def run_worker(w, hg, edge, dtype, halo):
+def run_worker(w, rows_per_rank, edge, dtype, halo, extra_rows=1):
     world = min(n_gpus(), 8)
     assert world >= 2
-    port = 29700 + (os.getpid() + hg + len(halo)) % 1000
+    hg = rows_per_rank * world + extra_rows          # uneven split: the slabs differ by one row
+    port = 29700 + (os.getpid() + hg + w + len(halo)) % 1000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "_multigpu_worker.py"), str(w), str(hg), "12", str(edge), dtype, halo]
@@ -28,17 +29,24 @@ def run_worker(w, hg, edge, dtype, halo):
     assert "MULTIGPU_OK" in res.stdout
 
 
-@pytest.mark.parametrize("w,hg,edge,dtype", [(256, 96, 1, "f32"), (260, 50, 0, "f64"), (1024, 64, 1, "f64"),
-                                             (37, 21, 1, "f32")])
-def test_sharded_equals_unsharded(w, hg, edge, dtype):
-    run_worker(w, hg, edge, dtype, "nccl")
+# (width, rows per rank, edge, dtype): slabs of >= 32 rows advance two steps per pass, smaller ones one;
+# 37 is a ragged width (scalar kernel), 260 a vector width that ends mid-warp
+@pytest.mark.parametrize("w,rows,edge,dtype", [(256, 48, 1, "f32"), (260, 25, 0, "f64"), (1024, 33, 1, "f64"),
+                                               (37, 10, 1, "f32"), (2048, 40, 0, "f32"), (512, 2, 1, "f32")])
+def test_sharded_equals_unsharded(w, rows, edge, dtype):
+    run_worker(w, rows, edge, dtype, "nccl")
 
 
-@pytest.mark.parametrize("w,hg,edge,dtype", [(256, 96, 1, "f32"), (260, 50, 0, "f64"), (1024, 16, 1, "f64"),
-                                             (4096, 40, 0, "f32")])
-def test_sharded_with_fused_peer_memory_halo_equals_unsharded(w, hg, edge, dtype):
-    """The face kernel stores the halo into the neighbours' ghost rows itself (cudaIpc + NVLink)."""
-    run_worker(w, hg, edge, dtype, "p2p")
+# the fused slab kernels need >= 256 vectors per row and >= 4 rows per slab
+@pytest.mark.parametrize("w,rows,edge,dtype", [(1024, 48, 1, "f32"), (1024, 33, 0, "f64"), (4096, 40, 0, "f32"),
+                                               (2048, 5, 1, "f32"), (1536, 37, 1, "f64")])
+def test_sharded_with_fused_peer_memory_halo_equals_unsharded(w, rows, edge, dtype):
+    """The slab kernels store the halo into the neighbours' ghost rows themselves (cudaIpc + NVLink)."""
+    run_worker(w, rows, edge, dtype, "p2p")
+
+
+def test_one_row_per_rank_uses_the_one_row_halo():
+    run_worker(64, 1, 0, "f32", "nccl", extra_rows=0)
 
 
 @pytest.mark.parametrize("p2p", [True, False])
