@@ -82,6 +82,7 @@ PROTOTYPES = {
     "chemsim_lbm_step_kernel_name": (C.c_char_p, [_H]),
     "chemsim_lbm_barrier": (_I, [_H]),
     "chemsim_lbm_set_p2p_timeout": (_I, [_H, _D]),
+    "chemsim_lbm_set_stream_convention": (_I, [_H, _I]),
     "chemsim_lbm_fill_geometry": (_I, [_H, _I]),
     "chemsim_lbm_paint_rect": (_I, [_H, _I, _I, _I, _I, _I]),
     "chemsim_lbm_get_async": (_I, [_H, _I, _I, _P, _P, _SZ]),

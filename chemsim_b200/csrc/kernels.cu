@@ -169,6 +169,19 @@ __global__ void paint_rect_kernel(uint8_t *mask, int mask_pitch, int x0, int y0,
     if (x < w && y < h) mask[(size_t)(y0 + y) * mask_pitch + x0 + x] = value;
 }
 
+// Element-wise reversal of a dense buffer of n elements of `size` bytes (1, 4, 8): the point
+// reflection (y, x) <-> (H-1-y, W-1-x) of a row-major field is the reversal of its flat array.
+// Used at the host boundary when the mirrored stream convention is selected.
+template <typename E>
+__global__ void reverse_kernel(E *data, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += (size_t)gridDim.x * blockDim.x) {
+        const E a = data[i], b = data[n - 1 - i];
+        data[i] = b;
+        data[n - 1 - i] = a;
+    }
+}
+
 // ---- device-side render.rs -----------------------------------------------------
 // The scalar a render mode normalises: render_scalar_field (src/render.rs:23-89) uses
 // the field itself, render_vector_field (:91-178) uses mag = vx*vx + vy*vy.
@@ -461,6 +474,18 @@ int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin,
     const int segs = (W + MASK_SEGMENT - 1) / MASK_SEGMENT;
     const int blocks = reduction_blocks((size_t)rows * segs);
     mask_flags_kernel<<<blocks, RED_THREADS, 0, s>>>(mask, mask_pitch, W, row_begin, rows, flags, flag_pitch, any);
+    const int e = check_launch();
+    return e ? e : 1;
+}
+
+int launch_reverse(void *data, size_t n, int elem_bytes, cudaStream_t s)
+{
+    if (n < 2) return 0;
+    const int blocks = reduction_blocks(n / 2);
+    if (elem_bytes == 1)      reverse_kernel<uint8_t><<<blocks, RED_THREADS, 0, s>>>((uint8_t *)data, n);
+    else if (elem_bytes == 4) reverse_kernel<uint32_t><<<blocks, RED_THREADS, 0, s>>>((uint32_t *)data, n);
+    else if (elem_bytes == 8) reverse_kernel<unsigned long long><<<blocks, RED_THREADS, 0, s>>>((unsigned long long *)data, n);
+    else return -(int)cudaErrorInvalidValue;
     const int e = check_launch();
     return e ? e : 1;
 }

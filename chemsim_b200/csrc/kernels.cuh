@@ -136,6 +136,8 @@ constexpr int MASK_SEGMENT = 64;   // cells per mask-flag byte
 int launch_mask_flags(const uint8_t *mask, int mask_pitch, int W, int row_begin, int rows, uint8_t *flags,
                       int flag_pitch, int *any, cudaStream_t s);
 
+// reverse a dense device buffer of n elements of elem_bytes (1, 4 or 8) bytes in place
+int launch_reverse(void *data, size_t n, int elem_bytes, cudaStream_t s);
 // set mask cells [y0, y0+h) x [x0, x0+w) (already clipped to the slab) to `value`
 int launch_paint_rect(uint8_t *mask, int mask_pitch, int x0, int y0, int w, int h, uint8_t value, cudaStream_t s);
 

@@ -617,6 +617,9 @@ int readout_impl(chemsim_lbm *h, int kind, int q, void *dst0, void *dst1)
     const int rs = ensure_stage(h, dst1 ? 2 : 1, bytes);
     if (rs) return rs;
     LAUNCH_TRY(h, launch_readout<T>(readout_args<T>(h, kind, q, h->stage[0], h->stage[1]), h->stream));
+    if (h->stream_mirrored)
+        for (int i = 0; i < (dst1 ? 2 : 1); ++i)
+            LAUNCH_TRY(h, launch_reverse(h->stage[i], (size_t)h->W * h->H, (int)sizeof(T), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(dst0, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
     if (dst1) CUDA_TRY(h, cudaMemcpyAsync(dst1, h->stage[1], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -655,6 +658,9 @@ int snapshot_async_impl(chemsim_lbm *h, int field, int q, void *dst0, void *dst1
                                       READ_EQUILIBRIUM, READ_NON_EQUILIBRIUM};
         LAUNCH_TRY(h, launch_readout<T>(readout_args<T>(h, kind_of[field], q, s0, two ? s1 : nullptr), h->stream));
     }
+    if (h->stream_mirrored)
+        for (int i = 0; i < (two ? 2 : 1); ++i)
+            LAUNCH_TRY(h, launch_reverse(i ? s1 : s0, (size_t)h->W * h->H, (int)sizeof(T), h->stream));
     CUDA_TRY(h, cudaEventRecord(h->ev_snap_ready[slot], h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_snap_ready[slot], 0));
     CUDA_TRY(h, cudaMemcpyAsync(dst0, s0, bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
@@ -682,6 +688,11 @@ int init_equilibrium_rows(chemsim_lbm *h, int row_begin, int row_count, const vo
     CUDA_TRY(h, cudaMemcpyAsync(h->stage[0], rho, bytes, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->stage[1], vx, bytes, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->stage[2], vy, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (h->stream_mirrored) {           // host rows [b, b+n) are the reflected device rows [H-b-n, H-b), reversed
+        for (int i = 0; i < 3; ++i)
+            LAUNCH_TRY(h, launch_reverse(h->stage[i], (size_t)h->W * row_count, (int)h->esize, h->stream));
+        row_begin = h->H - row_begin - row_count;
+    }
     if (h->dtype == CHEMSIM_LBM_F32)
         LAUNCH_TRY(h, launch_init_equilibrium<float>((const float *)h->stage[0], (const float *)h->stage[1],
                                                      (const float *)h->stage[2], (float *)h->buf[h->cur], h->plane,
@@ -699,6 +710,16 @@ int init_equilibrium_rows(chemsim_lbm *h, int row_begin, int row_count, const vo
 // Upload mask rows on stream `s`, refresh their segment flags; *d_flag |= any solid.
 int upload_geometry_rows(chemsim_lbm *h, int row_begin, int row_count, const uint8_t *solid, cudaStream_t s)
 {
+    if (h->stream_mirrored) {           // through a dense staging copy, reversed (main stream only)
+        const size_t n = (size_t)h->W * row_count;
+        const int rs = ensure_stage(h, 1, n);
+        if (rs) return rs;
+        CUDA_TRY(h, cudaMemcpyAsync(h->stage[0], solid, n, cudaMemcpyHostToDevice, s));
+        LAUNCH_TRY(h, launch_reverse(h->stage[0], n, 1, s));
+        row_begin = h->H - row_begin - row_count;
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->mask + (size_t)row_begin * h->mask_pitch, h->mask_pitch, h->stage[0], h->W, h->W,
+                                      row_count, cudaMemcpyDeviceToDevice, s));
+    } else
     CUDA_TRY(h, cudaMemcpy2DAsync(h->mask + (size_t)row_begin * h->mask_pitch, h->mask_pitch, solid, h->W, h->W,
                                   row_count, cudaMemcpyHostToDevice, s));
     LAUNCH_TRY(h, launch_mask_flags(h->mask, h->mask_pitch, h->W, row_begin, row_count, h->mask_flags, h->flag_pitch,
@@ -1098,6 +1119,15 @@ int chemsim_lbm_set_population(chemsim_lbm_t *h, int q, const void *src, size_t 
     BIND(h);
     const int c = check_n(h, n);
     if (c) return c;
+    if (h->stream_mirrored) {
+        const size_t bytes = n * h->esize;
+        const int rs = ensure_stage(h, 1, bytes);
+        if (rs) return rs;
+        CUDA_TRY(h, cudaMemcpyAsync(h->stage[0], src, bytes, cudaMemcpyHostToDevice, h->stream));
+        LAUNCH_TRY(h, launch_reverse(h->stage[0], n, (int)h->esize, h->stream));
+        CUDA_TRY(h, cudaMemcpy2DAsync(row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize, h->stage[0], (size_t)h->W * h->esize,
+                                      (size_t)h->W * h->esize, h->H, cudaMemcpyDeviceToDevice, h->stream));
+    } else
     CUDA_TRY(h, cudaMemcpy2DAsync(row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize, src, (size_t)h->W * h->esize,
                                   (size_t)h->W * h->esize, h->H, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1140,6 +1170,12 @@ int chemsim_lbm_set_geometry_async(chemsim_lbm_t *h, const uint8_t *solid, size_
     BIND(h);
     const int c = check_n(h, n);
     if (c) return c;
+    if (h->stream_mirrored) {           // staging + reversal live on the main stream: ordered, not overlapped
+        const int r = upload_geometry_rows(h, 0, h->H, solid, h->stream);
+        if (r) return r;
+        h->has_mask = 1;
+        return CHEMSIM_LBM_OK;
+    }
     // the copy stream may not overwrite the mask while queued steps still read it
     CUDA_TRY(h, cudaEventRecord(h->ev_main, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_main, 0));
@@ -1168,6 +1204,7 @@ int chemsim_lbm_paint_rect(chemsim_lbm_t *h, int x0, int y0, int width, int heig
     if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
     if (width < 0 || height < 0) return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "negative rectangle size");
     BIND(h);
+    if (h->stream_mirrored) { x0 = h->W - x0 - width; y0 = h->Hglobal - y0 - height; }
     // clip to the lattice in x and to this handle's slab in y (y is a GLOBAL row)
     long long xa = x0, xb = (long long)x0 + width, ya = (long long)y0 - h->row0, yb = ya + height;
     if (xa < 0) xa = 0;
@@ -1190,6 +1227,19 @@ int chemsim_lbm_barrier(chemsim_lbm_t *h)
     BIND(h);
     NCCL_TRY(h, nccl_dyn().AllReduce(h->d_scalar + 4, h->d_scalar + 5, 1, ncclDouble, ncclSum, h->comm, h->stream));
     h->launches += 1;
+    return CHEMSIM_LBM_OK;
+}
+
+int chemsim_lbm_set_stream_convention(chemsim_lbm_t *h, int mirrored)
+{
+    if (!h) return CHEMSIM_LBM_ERR_INVALID_ARGUMENT;
+    if (mirrored && h->nranks > 1)
+        return fail(h, CHEMSIM_LBM_ERR_UNSUPPORTED,
+                    "mirrored stream convention on a sharded lattice: create the slabs in reversed rank order instead "
+                    "(the reflection maps slab r onto slab nranks-1-r)");
+    if (h->have_populations && (mirrored != 0) != (h->stream_mirrored != 0))
+        return fail(h, CHEMSIM_LBM_ERR_INVALID_ARGUMENT, "select the stream convention before the first upload");
+    h->stream_mirrored = mirrored ? 1 : 0;
     return CHEMSIM_LBM_OK;
 }
 
@@ -1284,6 +1334,15 @@ int chemsim_lbm_get_population(chemsim_lbm_t *h, int q, void *dst, size_t n)
     const int c = check_n(h, n);
     if (c) return c;
     if (!h->have_populations) return fail(h, CHEMSIM_LBM_ERR_NOT_READY, "populations not set");
+    if (h->stream_mirrored) {
+        const size_t bytes = n * h->esize;
+        const int rs = ensure_stage(h, 1, bytes);
+        if (rs) return rs;
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->stage[0], (size_t)h->W * h->esize, row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize,
+                                      (size_t)h->W * h->esize, h->H, cudaMemcpyDeviceToDevice, h->stream));
+        LAUNCH_TRY(h, launch_reverse(h->stage[0], n, (int)h->esize, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(dst, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else
     CUDA_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->W * h->esize, row_ptr(h, h->cur, q, 0), (size_t)h->pitch * h->esize,
                                   (size_t)h->W * h->esize, h->H, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1309,6 +1368,13 @@ int chemsim_lbm_get_geometry(chemsim_lbm_t *h, uint8_t *dst, size_t n)
     BIND(h);
     const int c = check_n(h, n);
     if (c) return c;
+    if (h->stream_mirrored) {
+        const int rs = ensure_stage(h, 1, n);
+        if (rs) return rs;
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->stage[0], h->W, h->mask, h->mask_pitch, h->W, h->H, cudaMemcpyDeviceToDevice, h->stream));
+        LAUNCH_TRY(h, launch_reverse(h->stage[0], n, 1, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(dst, h->stage[0], n, cudaMemcpyDeviceToHost, h->stream));
+    } else
     CUDA_TRY(h, cudaMemcpy2DAsync(dst, h->W, h->mask, h->mask_pitch, h->W, h->H, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return CHEMSIM_LBM_OK;
@@ -1378,6 +1444,7 @@ int chemsim_lbm_render(chemsim_lbm_t *h, int mode, int overlay_geometry, uint8_t
     else
         LAUNCH_TRY(h, launch_render_image<double>((const double *)h->buf[h->cur], h->plane, h->pitch, h->W, h->H, mode,
                                                   stats, mask, h->mask_pitch, (uchar4 *)h->stage[0], h->stream));
+    if (h->stream_mirrored) LAUNCH_TRY(h, launch_reverse(h->stage[0], n_pixels, 4, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(rgba, h->stage[0], bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     P2P_CHECK(h);

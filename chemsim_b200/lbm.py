@@ -376,6 +376,10 @@ class State:
         """Device-side barrier over the ranks of a sharded lattice (asynchronous, collective)."""
         self._check(self._lib.chemsim_lbm_barrier(self._h))
 
+    def set_stream_convention(self, mirrored: bool):
+        """Select how af::convolve2's flip is read (include/chemsim_lbm.h); before the first upload."""
+        self._check(self._lib.chemsim_lbm_set_stream_convention(self._h, int(bool(mirrored))))
+
     def set_p2p_timeout(self, seconds: float):
         self._check(self._lib.chemsim_lbm_set_p2p_timeout(self._h, float(seconds)))
 

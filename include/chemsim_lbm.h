@@ -163,6 +163,18 @@ int chemsim_lbm_shape(const chemsim_lbm_t *h, int *width, int *local_height, int
  * lattice dtype exactly as src/lbm.rs:54-56, :64-66, :84 compute them. */
 int chemsim_lbm_set_discretization(chemsim_lbm_t *h, double delta_x, double delta_t);
 
+/* Which way State::stream moves the populations.  The reference streams with
+ * af::convolve2(f_i, stencil_i^T) (src/lbm.rs:722-724).  0 (default): a true, flipped convolution centred
+ * at floor(3/2) — ArrayFire 3.6's documented behaviour — which moves population i by
+ * (dy, dx) = (-c_ix, +c_iy) in [y][x] memory terms.  1: the other reading (the stencil
+ * applied unflipped), which moves every population the opposite way.  The two differ by a point reflection
+ * of the lattice, (y, x) <-> (H-1-y, W-1-x), so convention 1 runs the same kernels and reverses every field
+ * at this boundary (uploads, readouts, geometry, render, paint_rect coordinates).  Parity with the real
+ * reference is unpinned (no Rust/ArrayFire in the build image): a reference-generated golden vector
+ * (rust/tools/dump_golden.rs, tests/test_reference_golden.py) decides, and this switch makes the outcome a
+ * flag instead of a rewrite.  Select it before the first upload; unsharded lattices only. */
+int chemsim_lbm_set_stream_convention(chemsim_lbm_t *h, int mirrored);
+
 /* collision = Box::new(BGK { tau })  (src/lbm.rs:345-347; factor = -dt/tau, :357) */
 int chemsim_lbm_set_bgk(chemsim_lbm_t *h, double tau);
 

@@ -20,7 +20,7 @@ the numpy array `s.reshape(h, w)`, indexed [y, x].
 from __future__ import annotations
 
 import numpy as np
-from scipy.signal import convolve2d
+from scipy.signal import convolve2d, correlate2d
 
 # src/lbm.rs:209-219 (numerators over 36), :221-231
 W_NUM = [16, 4, 4, 4, 4, 1, 1, 1, 1]
@@ -124,15 +124,20 @@ def equilibrium(f, k: Consts):
     return compute_equilibrium(density(f), vx, vy, k)
 
 
-def stream(f, periodic=False):
-    """src/lbm.rs:716-729.  periodic=True is the extension (boundary='wrap')."""
+def stream(f, periodic=False, mirrored=False):
+    """src/lbm.rs:716-729.  periodic=True is the extension (boundary='wrap').
+    mirrored=True is the OTHER reading of af::convolve2 — the kernel applied unflipped (a
+    correlation) — which moves every population the opposite way; the product's switch for it is
+    chemsim_lbm_set_stream_convention (a reference-generated golden vector decides, see
+    tests/test_reference_golden.py)."""
+    conv = correlate2d if mirrored else convolve2d
     out = []
     for i in range(9):
         st = stencil_matrix(i, f.dtype).T  # pair.0.stencil.transpose()
         if periodic:
-            o = convolve2d(f[i], st, mode="same", boundary="wrap")
+            o = conv(f[i], st, mode="same", boundary="wrap")
         else:
-            o = convolve2d(f[i], st, mode="same", boundary="fill", fillvalue=0)
+            o = conv(f[i], st, mode="same", boundary="fill", fillvalue=0)
         out.append(o.astype(f.dtype))
     return np.stack(out)
 
@@ -217,9 +222,9 @@ def collide_kbc(f, feq, k: Consts, visc):
     return np.stack(out)
 
 
-def step(f, solid, k: Consts, collision=("bgk", 15.0), periodic=False):
+def step(f, solid, k: Consts, collision=("bgk", 15.0), periodic=False, mirrored=False):
     """State::step src/lbm.rs:694-714: stream -> bounce_back -> collide."""
-    f = stream(f, periodic)
+    f = stream(f, periodic, mirrored)
     f = bounce_back(f, solid)
     feq = equilibrium(f, k)
     kind = collision[0]
