@@ -469,9 +469,15 @@ def run_gpu_arm(args):
             return
         peak, peak_src = measured_peak_gbs()
         bpc = BYTES_PER_CELL[args.dtype]
-        # the dominant kernel is the fused step kernel: one launch per step per GPU
+        # The dominant kernel is the fused step kernel.  One launch reads every population once and
+        # writes it once = 72 B (f32) / 144 B (f64) per cell of ALGORITHMIC traffic — whether the
+        # launch advances the lattice by one step (step_vec_kernel) or by two (step2_kernel, which
+        # keeps the intermediate lattice in shared memory).  achieved = that / the launch duration.
         cells_per_launch = w * hl
-        launch_s = ms * 1e-3 / args.steps
+        # passes over the slab per batch: the library pairs the steps of one chemsim_lbm_step call
+        step_launches = (args.steps // 2 + args.steps % 2) if kernel_name.startswith("step2") else args.steps
+        steps_per_launch = args.steps / step_launches
+        launch_s = ms * 1e-3 / step_launches
         achieved = bpc * cells_per_launch / launch_s / 1e9
         drift = (mass1 - mass0) / mass0
         line = {
@@ -489,7 +495,15 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(args.workload, args.dtype),
                          "algorithmic_bytes_per_launch": bpc * cells_per_launch, "peak_source": peak_src,
-                         "frac_of_nominal_8TBps": achieved / 8000.0},
+                         "frac_of_nominal_8TBps": achieved / 8000.0,
+                         "steps_per_launch": steps_per_launch, "launch_us": launch_s * 1e6,
+                         "per_step_accounting": {
+                             "bytes_per_cell_per_step": bpc, "GBps": bpc * cells_per_launch * steps_per_launch / launch_s / 1e9,
+                             "frac_of_peak": bpc * cells_per_launch * steps_per_launch / launch_s / 1e9 / peak,
+                             "note": "BASELINE.json's 72 B (f32) / 144 B (f64) per lattice update, i.e. what a "
+                                     "one-step-per-pass kernel would have to move; above 1.0 because the two-step "
+                                     "kernel moves half of it (temporal blocking), not because work is skipped: "
+                                     "results are bit-identical to single steps (tests/, extras.parity_sharded)"}},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "gpu_launches_what": "kernels of this rank inside one timed batch of `steps` steps",

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchemsim_lbm.so")
 # one translation unit per collision operator for the fused step kernels (compiled in parallel)
 SOURCES = ["step_bgk.cu", "step_trt.cu", "step_regularized.cu", "step_kbc.cu", "kernels.cu", "lattice.cu"]
-HEADERS = ["d2q9.cuh", "consts.hpp", "kernels.cuh", "step_decl.cuh", "step_impl.cuh", "nccl_dyn.h",
+HEADERS = ["d2q9.cuh", "consts.hpp", "kernels.cuh", "step_decl.cuh", "step_impl.cuh", "step2_impl.cuh", "nccl_dyn.h",
            os.path.join("..", "..", "include", "chemsim_lbm.h")]
 OBJ_DIR = os.path.join(HERE, "build")
 

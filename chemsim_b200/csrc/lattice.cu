@@ -1566,8 +1566,20 @@ int chemsim_lbm_kernel_launches(const chemsim_lbm_t *h, uint64_t *out)
 const char *chemsim_lbm_step_kernel_name(const chemsim_lbm_t *h)
 {
     if (!h) return "";
-    return h->dtype == CHEMSIM_LBM_F32 ? step_kernel_name<float>(step_args<float>(h, 0, h->H))
-                                       : step_kernel_name<double>(step_args<double>(h, 0, h->H));
+    const bool f32 = h->dtype == CHEMSIM_LBM_F32;
+    // what a batch of >= 2 steps launches: the two-step kernel where it applies (an odd last step and
+    // the lattices it does not support take the single-step kernel)
+    const bool two = f32 ? step2_supported(step_args<float>(h, 0, h->H)) : step2_supported(step_args<double>(h, 0, h->H));
+    const int TY = f32 ? step2_tile_rows<float>() : step2_tile_rows<double>();
+    if (h->nranks == 1) {
+        if (two) return f32 ? "step2_kernel<float>" : "step2_kernel<double>";
+    } else if (two && deep_halo(h) && h->Hglobal / h->nranks >= 2 * TY) {
+        if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) return f32 ? "step2_slab_p2p_kernel<float>" : "step2_slab_p2p_kernel<double>";
+        return f32 ? "step2_kernel<float>" : "step2_kernel<double>";
+    } else if (h->halo_mode == CHEMSIM_LBM_HALO_P2P) {
+        return f32 ? "step_slab_p2p_kernel<float>" : "step_slab_p2p_kernel<double>";
+    }
+    return f32 ? step_kernel_name<float>(step_args<float>(h, 0, h->H)) : step_kernel_name<double>(step_args<double>(h, 0, h->H));
 }
 
 }  // extern "C"

@@ -38,7 +38,7 @@ template <int V> __host__ __device__ constexpr int shift_of(int q) { return (((e
 
 // One tile: rows [ty0, ty0+TY) x columns [tx0, tx0+TX); rows >= y_end are not stored (tile rows
 // that overlap the next region).  P2P: also deliver the face rows to the neighbours.
-template <typename T, bool PERIODIC_X, int COL, bool P2P>
+template <typename T, bool PERIODIC_X, int COL, bool P2P, bool USE_MASK>
 __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, const int tx0, const int ty0,
                                            const int y_end, const int tok)
 {
@@ -47,10 +47,10 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
     const int tid = threadIdx.x;
     const T *src = a.src + tok;
     const uint8_t *mask = a.mask + tok;
-    // does any cell this tile touches need the mask?  own rows: if the slab has solids; ghost rows
-    // (tiles at a slab face): the neighbour may have solids there even if this slab has none
-    const bool touches_ghost = ty0 == 0 || ty0 + TY >= a.H;
-    const bool use_mask = a.has_mask != 0 || (a.ghost_mask != 0 && touches_ghost);
+    // USE_MASK: does any cell this tile touches need the mask?  Own rows: if the slab has solids;
+    // ghost rows (tiles at a slab face): the neighbour may have solids there even if this slab has
+    // none, so face tiles of a y-slab always take the masked instantiation (see the launchers).
+    constexpr bool use_mask = USE_MASK;
 
     // ---- phase A: step n+1 on the ext region -> shared memory -----------------------------------
     // interior tile: every source cell of the ext region lies inside this slab (no wrap, no
@@ -189,7 +189,7 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
 }
 
 // rows [y_begin, y_begin + y_count) advance by two steps (unsharded lattice, or one region of a slab)
-template <typename T, bool PERIODIC_X, int COL>
+template <typename T, bool PERIODIC_X, int COL, bool USE_MASK>
 __global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
 step2_kernel(const __grid_constant__ StepArgs<T> a)
 {
@@ -199,13 +199,13 @@ step2_kernel(const __grid_constant__ StepArgs<T> a)
     const int y_end = a.y_begin + a.y_count;
     const int ty0 = a.y_begin + (blockIdx.z * gridDim.y + blockIdx.y) * TL::TY;
     if (ty0 >= y_end) return;
-    step2_tile<T, PERIODIC_X, COL, false>(a, reinterpret_cast<T *>(smem_raw), blockIdx.x * TL::TX, ty0, y_end,
-                                          order_after_grid_dependency());
+    step2_tile<T, PERIODIC_X, COL, false, USE_MASK>(a, reinterpret_cast<T *>(smem_raw), blockIdx.x * TL::TX, ty0, y_end,
+                                                    order_after_grid_dependency());
 }
 
 // a whole y-slab, H >= 2 TY: tile-row slot 0 -> rows [0, TY), slot 1 -> rows [H-TY, H) (the two face
 // tile rows, dispatched first), slot s >= 2 -> rows [(s-1) TY, ...) clipped at H-TY
-template <typename T, bool PERIODIC_X, int COL>
+template <typename T, bool PERIODIC_X, int COL, bool USE_MASK>
 __global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
 step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
 {
@@ -218,13 +218,13 @@ step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     if (slot >= 2) {                                 // interior tile row: no ghost row, feeds no neighbour
         const int ty0 = (slot - 1) * TL::TY;
         if (ty0 >= a.H - TL::TY) return;
-        step2_tile<T, PERIODIC_X, COL, false>(a, sm, tx0, ty0, a.H - TL::TY, order_after_grid_dependency());
+        step2_tile<T, PERIODIC_X, COL, false, USE_MASK>(a, sm, tx0, ty0, a.H - TL::TY, order_after_grid_dependency());
         return;
     }
     const HaloP2P &p = a.halo;
     const int ty0 = slot == 0 ? 0 : a.H - TL::TY;
     const int tok = order_after_grid_dependency() + order_after_halo_flags(p, slot == 0, slot == 1);
-    step2_tile<T, PERIODIC_X, COL, true>(a, sm, tx0, ty0, ty0 + TL::TY, tok);
+    step2_tile<T, PERIODIC_X, COL, true, true>(a, sm, tx0, ty0, ty0 + TL::TY, tok);      // ghost rows: always masked
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) publish_step(p, 2u * gridDim.x, 2u);
@@ -246,13 +246,16 @@ void launch_step2_col(const StepArgs<T> &a, cudaStream_t s)
     using TL = Step2Tile<T>;
     const dim3 block(TL::NT);
     const dim3 grid = row_grid((a.W + TL::TX - 1) / TL::TX, (a.y_count + TL::TY - 1) / TL::TY);
-    if (a.periodic_x) {
-        step2_opt_in(step2_kernel<T, true, COL>, TL::SMEM);
-        launch_chained(step2_kernel<T, true, COL>, grid, block, s, a, TL::SMEM);
-    } else {
-        step2_opt_in(step2_kernel<T, false, COL>, TL::SMEM);
-        launch_chained(step2_kernel<T, false, COL>, grid, block, s, a, TL::SMEM);
-    }
+    // a region at a slab face recomputes ghost-row cells, whose solid flags the neighbour owns
+    const bool masked = a.has_mask != 0 || (a.ghost_mask != 0 && (a.y_begin == 0 || a.y_begin + a.y_count >= a.H));
+#define CHEMSIM_LAUNCH_STEP2(PX, M)                                                           \
+    do {                                                                                      \
+        step2_opt_in(step2_kernel<T, PX, COL, M>, TL::SMEM);                                  \
+        launch_chained(step2_kernel<T, PX, COL, M>, grid, block, s, a, TL::SMEM);             \
+    } while (0)
+    if (a.periodic_x) { if (masked) CHEMSIM_LAUNCH_STEP2(true, true); else CHEMSIM_LAUNCH_STEP2(true, false); }
+    else              { if (masked) CHEMSIM_LAUNCH_STEP2(false, true); else CHEMSIM_LAUNCH_STEP2(false, false); }
+#undef CHEMSIM_LAUNCH_STEP2
 }
 
 // the whole slab, two steps, with the peer-memory halo (H >= 2 TY)
@@ -263,13 +266,14 @@ void launch_slab_p2p2_col(const StepArgs<T> &a, cudaStream_t s)
     const dim3 block(TL::NT);
     const int interior_rows = a.H - 2 * TL::TY;
     const dim3 grid = row_grid((a.W + TL::TX - 1) / TL::TX, 2 + (interior_rows + TL::TY - 1) / TL::TY);
-    if (a.periodic_x) {
-        step2_opt_in(step2_slab_p2p_kernel<T, true, COL>, TL::SMEM);
-        launch_chained(step2_slab_p2p_kernel<T, true, COL>, grid, block, s, a, TL::SMEM);
-    } else {
-        step2_opt_in(step2_slab_p2p_kernel<T, false, COL>, TL::SMEM);
-        launch_chained(step2_slab_p2p_kernel<T, false, COL>, grid, block, s, a, TL::SMEM);
-    }
+#define CHEMSIM_LAUNCH_STEP2(PX, M)                                                           \
+    do {                                                                                      \
+        step2_opt_in(step2_slab_p2p_kernel<T, PX, COL, M>, TL::SMEM);                         \
+        launch_chained(step2_slab_p2p_kernel<T, PX, COL, M>, grid, block, s, a, TL::SMEM);    \
+    } while (0)
+    if (a.periodic_x) { if (a.has_mask) CHEMSIM_LAUNCH_STEP2(true, true); else CHEMSIM_LAUNCH_STEP2(true, false); }
+    else              { if (a.has_mask) CHEMSIM_LAUNCH_STEP2(false, true); else CHEMSIM_LAUNCH_STEP2(false, false); }
+#undef CHEMSIM_LAUNCH_STEP2
 }
 
 }  // namespace chemsim

@@ -227,7 +227,7 @@ def test_full_size_4096_against_oracle_and_mass(dtype):
     rho, vx, vy, solid = scenarios.smooth_periodic(w, h, dtype)
     state = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=lbm.EDGE_PERIODIC)
     state.init_equilibrium(rho, vx, vy)
-    assert "vec" in state.step_kernel_name()
+    assert "scalar" not in state.step_kernel_name()          # a vector-width kernel (step2 or step_vec)
     m0 = state.total_mass()
     state.step(2)
     f_ref = O.step_fused(O.compute_equilibrium(rho, vx, vy), None, 2, 0.8, O.EDGE_PERIODIC)
@@ -499,7 +499,7 @@ def test_paint_brush_on_the_device_equals_the_host_rewrite(dtype):
     state.step(2)
     f_ref = O.step_fused(f_ref, np.zeros_like(solid), 2, 0.8, O.EDGE_ZEROFILL)
     assert_parity(state.populations_array(), f_ref, "after fill_geometry(False)")
-    assert "vec" in state.step_kernel_name()
+    assert "scalar" not in state.step_kernel_name()          # a vector-width kernel (step2 or step_vec)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -617,3 +617,61 @@ def test_regularized_reports_the_underlying_viscosity_with_the_state_discretizat
     _ffi.check(_ffi.load().chemsim_lbm_kinematic_shear_viscosity(state._h, C.byref(out)), state._h)
     assert np.float32(out.value) == lbm.BGK(0.9).kinematic_shear_viscosity(disc, np.float32)
     assert _ffi.load().chemsim_lbm_kinematic_bulk_viscosity(state._h, None) == _ffi.ERR_INVALID_ARGUMENT
+
+
+# ---- the other reading of af::convolve2 (chemsim_lbm_set_stream_convention) --------------------------
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("edge", [lbm.EDGE_ZEROFILL, lbm.EDGE_PERIODIC])
+def test_mirrored_stream_convention_matches_the_correlation_restatement(dtype, edge):
+    """Convention 1 = the stencil applied unflipped: compared with oracle/lbm_numpy.py's literal
+    scipy.signal.correlate2d calls (an implementation that shares nothing with the switch, which
+    reverses the fields at the C-ABI boundary), for populations, every readout, the geometry, the
+    painted rectangle and the rendered image."""
+    from oracle import lbm_numpy as N
+    w, h = 44, 19
+    rho, vx, vy, solid = scenarios.random_state(w, h, dtype, seed=81)
+    k = N.Consts(dtype, 1.0, 1.0)
+    periodic = edge == lbm.EDGE_PERIODIC
+    state = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=edge)
+    state.set_stream_convention(True)
+    state.init_equilibrium(rho, vx, vy)
+    state.geometry = solid
+    np.testing.assert_array_equal(state.geometry, solid.astype(bool))
+    f = N.compute_equilibrium(rho, vx, vy, k)
+    assert_parity(state.populations_array(), f, "initial state")
+    state.step(5)                                        # two double steps + one single
+    for _ in range(5):
+        f = N.step(f, solid.astype(bool), k, ("bgk", 0.8), periodic, mirrored=True)
+    assert_parity(state.populations_array(), f.astype(dtype), "mirrored stream, 5 steps")
+    assert_parity(state.density().array, N.density(f).astype(dtype), "density")
+    for got, ref, name in zip(state.velocity(), N.velocity(f, k), "xy"):
+        assert_parity(got.array, ref.astype(dtype), "velocity " + name)
+    # ... and it differs from convention 0 (otherwise the test proves nothing)
+    plain = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=edge)
+    plain.init_equilibrium(rho, vx, vy)
+    plain.geometry = solid
+    plain.step(5)
+    assert not np.array_equal(plain.populations_array(), state.populations_array())
+    # the same run equals the point reflection of convention 0 on reflected inputs
+    rev = lambda a: np.ascontiguousarray(a[..., ::-1, ::-1])
+    refl = lbm.State.create((w, h), lbm.BGK(0.8), dtype=dtype, edge=edge)
+    refl.init_equilibrium(rev(rho), rev(vx), rev(vy))
+    refl.geometry = rev(solid)
+    refl.step(5)
+    assert_parity(state.populations_array(), rev(refl.populations_array()), "reflection identity")
+    # explicit populations, painted rectangle, image
+    state.paint_rect(3, 2, 9, 4, True)
+    solid2 = solid.copy(); solid2[2:6, 3:12] = 1
+    np.testing.assert_array_equal(state.geometry, solid2.astype(bool))
+    for q in range(9):
+        state.set_population(q, f[q].astype(dtype))
+    assert_parity(state.populations_array(), f.astype(dtype), "set/get population")
+    img, img_refl = state.render(1), None
+    refl.geometry = rev(solid2)
+    for q in range(9):
+        refl.set_population(q, rev(f[q].astype(dtype)))
+    img_refl = refl.render(1)
+    assert int(np.abs(img.astype(np.int16) - img_refl[::-1, ::-1].astype(np.int16)).max()) <= 1
+    with pytest.raises(lbm.LbmError):
+        state.set_stream_convention(False)               # not after the upload
