@@ -99,7 +99,7 @@ struct BGK {              // src/lbm.rs:345-370
         return (d.delta_x * d.delta_x / (3.0f * d.delta_t * d.delta_t)) * (tau - d.delta_t / 2.0f);
     }
     Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
-    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_bgk(h, tau); }
+    int apply(chemsim_lbm_t *h, const Discretization &) const { return chemsim_lbm_set_bgk(h, tau); }
 };
 
 struct TRT {              // src/lbm.rs:374-451
@@ -117,14 +117,14 @@ struct TRT {              // src/lbm.rs:374-451
         return cs * cs * (tau_plus / d.delta_t - 0.5f);
     }
     Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
-    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_trt(h, tau_plus, tau_minus); }
+    int apply(chemsim_lbm_t *h, const Discretization &) const { return chemsim_lbm_set_trt(h, tau_plus, tau_minus); }
 };
 
 struct KBC {              // src/lbm.rs:455-590
     Scalar ks_viscosity;
     Scalar kinematic_shear_viscosity(const Discretization &) const { return ks_viscosity; }
     Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
-    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_kbc(h, ks_viscosity); }
+    int apply(chemsim_lbm_t *h, const Discretization &) const { return chemsim_lbm_set_kbc(h, ks_viscosity); }
 };
 
 template <typename C>
@@ -132,7 +132,8 @@ struct Regularized {      // src/lbm.rs:596-666: only the underlying operator's 
     C underlying;
     Scalar kinematic_shear_viscosity(const Discretization &d) const { return underlying.kinematic_shear_viscosity(d); }
     Scalar kinematic_bulk_viscosity(const Discretization &d) const { return 2.0f * kinematic_shear_viscosity(d) / 3.0f; }
-    int apply(chemsim_lbm_t *h) const { return chemsim_lbm_set_regularized(h, underlying.kinematic_shear_viscosity(Discretization())); }
+    // Regularized::kinematic_shear_viscosity(disc) = underlying's, with the State's discretization (:663-665)
+    int apply(chemsim_lbm_t *h, const Discretization &d) const { return chemsim_lbm_set_regularized(h, underlying.kinematic_shear_viscosity(d)); }
 };
 
 // Value of compute_equilibrium: kept as the generating fields and evaluated on the GPU
@@ -203,7 +204,7 @@ public:
         s.h_.reset(h, [](chemsim_lbm_t *p) { chemsim_lbm_destroy(p); });
         s.size_ = lattice.size; s.discretization = disc;
         check(chemsim_lbm_set_discretization(h, disc.delta_x, disc.delta_t), h);
-        check(collision.apply(h), h);                 // Box<dyn CollisionOperator<L>>, :674
+        check(collision.apply(h, disc), h);             // Box<dyn CollisionOperator<L>>, :674
         const Populations &p = lattice.populations;
         const size_t n = s.size_.first * s.size_.second;
         if (p.from_equilibrium)
@@ -242,6 +243,25 @@ public:
 
     // `pub geometry` field (:673): reassignable between steps, main.rs:77-89
     void set_geometry(const Geometry &g) { check(chemsim_lbm_set_geometry(h_.get(), g.data(), g.size()), h_.get()); }
+    // main.rs:71-91 (the mouse handler: the geometry becomes the 9x9 block around the cursor) without its host
+    // round trip: row = floor(pos[1]), column = floor(pos[0]); two small kernels on the device
+    void paint_brush(double pos_x, double pos_y)
+    {
+        const long row = (long)std::floor(pos_y), col = (long)std::floor(pos_x);
+        if (row < 0 || col < 0 || row >= (long)size_.second || col >= (long)size_.first) return;
+        check(chemsim_lbm_fill_geometry(h_.get(), 0), h_.get());
+        check(chemsim_lbm_paint_rect(h_.get(), (int)col - 4, (int)row - 4, 9, 9, 1), h_.get());
+    }
+    // the State as bytes (populations, geometry, time, step counter) and back
+    std::vector<unsigned char> checkpoint() const
+    {
+        size_t n = 0;
+        check(chemsim_lbm_checkpoint_bytes(h_.get(), &n), h_.get());
+        std::vector<unsigned char> blob(n);
+        check(chemsim_lbm_checkpoint(h_.get(), blob.data(), blob.size()), h_.get());
+        return blob;
+    }
+    void restore(const std::vector<unsigned char> &blob) { check(chemsim_lbm_restore(h_.get(), blob.data(), blob.size()), h_.get()); }
     Geometry geometry() const
     {
         Geometry g(size_.first * size_.second);

@@ -37,7 +37,7 @@ public:
             m.slabs_[r] = s;
             check(chemsim_lbm_shape(s, nullptr, &m.rows_[r], nullptr, &m.row0_[r]), s);
             check(chemsim_lbm_set_discretization(s, disc.delta_x, disc.delta_t), s);
-            check(collision.apply(s), s);
+            check(collision.apply(s, disc), s);
             const size_t off = (size_t)m.row0_[r] * w, cnt = (size_t)m.rows_[r] * w;   // slab rows are contiguous
             check(chemsim_lbm_init_equilibrium(s, p.density.get_underlying().data() + off,
                                                p.vx.get_underlying().data() + off, p.vy.get_underlying().data() + off,

@@ -2,6 +2,10 @@
 // No Triton, no multi-backend dispatch, no CPU fallback: if nvcc is missing the build fails.
 use std::{env, path::PathBuf, process::Command};
 
+// one translation unit per collision operator for the fused step kernels (chemsim_b200/build.py compiles them in parallel)
+const SOURCES: [&str; 6] = ["step_bgk.cu", "step_trt.cu", "step_regularized.cu", "step_kbc.cu", "kernels.cu", "lattice.cu"];
+const HEADERS: [&str; 7] = ["d2q9.cuh", "consts.hpp", "kernels.cuh", "step_decl.cuh", "step_impl.cuh", "step2_impl.cuh", "nccl_dyn.h"];
+
 fn main() {
     let manifest = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap());
     let csrc = manifest.join("..").join("chemsim_b200").join("csrc");
@@ -17,8 +21,7 @@ fn main() {
             "-cudart", "static", "-shared", "-o",
         ])
         .arg(&lib)
-        .arg(csrc.join("kernels.cu"))
-        .arg(csrc.join("lattice.cu"))
+        .args(SOURCES.iter().map(|f| csrc.join(f)))
         .arg("-ldl")
         .status()
         .expect("nvcc not found (set NVCC=/path/to/nvcc)");
@@ -26,7 +29,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=chemsim_lbm");
     println!("cargo:rustc-env=CHEMSIM_LBM_LIB_DIR={}", out.display());
-    for f in &["kernels.cu", "lattice.cu", "kernels.cuh", "d2q9.cuh", "nccl_dyn.h"] {
+    for f in SOURCES.iter().chain(HEADERS.iter()) {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", manifest.join("../include/chemsim_lbm.h").display());

@@ -4,6 +4,7 @@
 //! UNCOMPILED in this repository; the C++ twin `chemsim_b200/cpp/main_rs_harness.cpp` is what runs.
 use chemsim_lbm_b200::lbm::{self, CollisionOperator, Scalar};
 use chemsim_lbm_b200::matrix;
+use chemsim_lbm_b200::af_compat as af;
 
 struct LBMSim {
     speed_factor: usize,
@@ -32,7 +33,10 @@ fn initial_state(size: (usize, usize)) -> LBMSim {
     };
     let initial_density = matrix::Matrix::new_filled(1.0, size);                // main.rs:223
 
-    let pops = lbm::compute_equilibrium(initial_density, initial_velocity, &lbm::D2Q9::directions(), disc);
+    let pops = &({                                                              // main.rs:257-265, verbatim
+        let temp = lbm::compute_equilibrium(initial_density, initial_velocity, &lbm::D2Q9::directions(), disc);
+        temp.iter().map(|(_, pop)| pop.clone()).collect::<Vec<lbm::Population>>()
+    });
     let lattice = lbm::D2Q9::new(pops);                                         // main.rs:267
 
     let geometry = {                                                            // main.rs:269-312
@@ -47,7 +51,8 @@ fn initial_state(size: (usize, usize)) -> LBMSim {
                 if x == 0 || y == 0 || x == w - 1 || y == h - 1 { vec[y * w + x] = true; }
             }
         }
-        vec
+        let dim4 = af::Dim4::new(&[w as u64, h as u64, 1, 1]);                  // main.rs:308-311, verbatim
+        af::transpose(&af::Array::new(&vec[..], dim4), false)
     };
 
     let collision: Box<dyn CollisionOperator<lbm::D2Q9>> = Box::new(collision);
@@ -63,6 +68,7 @@ fn main() {
         for _ in 0..sim.speed_factor {                                          // main.rs:129-135
             sim.state.step();
         }
+        if frame == 250 { sim.state.paint_brush([200.5, 120.5]); }               // main.rs:71-91, on the device
         let image = sim.state.render_rgba(0, true);                             // main.rs:157-176, on the device
         if frame % 100 == 0 {
             println!("frame {} time {} mass {} first pixel {:?}", frame, sim.state.time, sim.state.total_mass(),

@@ -1,4 +1,4 @@
-//! `extern "C"` declarations of include/chemsim_lbm.h (ABI version 1).
+//! `extern "C"` declarations of include/chemsim_lbm.h (ABI version 2).
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_double, c_int, c_void};
 
@@ -45,8 +45,11 @@ extern "C" {
     pub fn chemsim_lbm_halo_mode(h: *const chemsim_lbm_t, mode: *mut c_int) -> c_int;
     pub fn chemsim_lbm_slab_rows(global_height: c_int, rank: c_int, nranks: c_int, row_offset: *mut c_int,
                                  rows: *mut c_int) -> c_int;
-    pub fn chemsim_lbm_halo_plan(rank: c_int, nranks: c_int, edge: c_int, out: *mut chemsim_lbm_halo_msg,
-                                 count: *mut c_int) -> c_int;
+    pub fn chemsim_lbm_halo_plan(global_height: c_int, rank: c_int, nranks: c_int, edge: c_int,
+                                 out: *mut chemsim_lbm_halo_msg, count: *mut c_int) -> c_int;
+    pub fn chemsim_lbm_barrier(h: *mut chemsim_lbm_t) -> c_int;
+    pub fn chemsim_lbm_set_p2p_timeout(h: *mut chemsim_lbm_t, seconds: c_double) -> c_int;
+    pub fn chemsim_lbm_set_stream_convention(h: *mut chemsim_lbm_t, mirrored: c_int) -> c_int;
     pub fn chemsim_lbm_destroy(h: *mut chemsim_lbm_t) -> c_int;
     pub fn chemsim_lbm_shape(h: *const chemsim_lbm_t, width: *mut c_int, local_height: *mut c_int,
                              global_height: *mut c_int, row_offset: *mut c_int) -> c_int;
@@ -70,12 +73,18 @@ extern "C" {
                                          solid: *const u8, n: usize) -> c_int;
     pub fn chemsim_lbm_set_geometry_async(h: *mut chemsim_lbm_t, solid: *const u8, n: usize) -> c_int;
 
+    pub fn chemsim_lbm_fill_geometry(h: *mut chemsim_lbm_t, value: c_int) -> c_int;
+    pub fn chemsim_lbm_paint_rect(h: *mut chemsim_lbm_t, x0: c_int, y0: c_int, width: c_int, height: c_int,
+                                  value: c_int) -> c_int;
+
     pub fn chemsim_lbm_step(h: *mut chemsim_lbm_t, nsteps: c_int) -> c_int;
     pub fn chemsim_lbm_synchronize(h: *mut chemsim_lbm_t) -> c_int;
     pub fn chemsim_lbm_time(h: *const chemsim_lbm_t, out: *mut c_double) -> c_int;
 
     pub fn chemsim_lbm_get_density(h: *mut chemsim_lbm_t, dst: *mut c_void, n: usize) -> c_int;
     pub fn chemsim_lbm_get_density_async(h: *mut chemsim_lbm_t, dst: *mut c_void, n: usize) -> c_int;
+    pub fn chemsim_lbm_get_async(h: *mut chemsim_lbm_t, field: c_int, q: c_int, dst0: *mut c_void, dst1: *mut c_void,
+                                 n: usize) -> c_int;
     pub fn chemsim_lbm_get_pressure(h: *mut chemsim_lbm_t, dst: *mut c_void, n: usize) -> c_int;
     pub fn chemsim_lbm_get_speed(h: *mut chemsim_lbm_t, dst: *mut c_void, n: usize) -> c_int;
     pub fn chemsim_lbm_get_velocity(h: *mut chemsim_lbm_t, vx: *mut c_void, vy: *mut c_void, n: usize) -> c_int;
@@ -90,6 +99,10 @@ extern "C" {
     pub fn chemsim_lbm_render(h: *mut chemsim_lbm_t, mode: c_int, overlay_geometry: c_int, rgba: *mut u8,
                               n_pixels: usize) -> c_int;
     pub fn chemsim_lbm_is_unstable(h: *mut chemsim_lbm_t, out: *mut c_int) -> c_int;
+
+    pub fn chemsim_lbm_checkpoint_bytes(h: *const chemsim_lbm_t, out: *mut usize) -> c_int;
+    pub fn chemsim_lbm_checkpoint(h: *mut chemsim_lbm_t, dst: *mut c_void, bytes: usize) -> c_int;
+    pub fn chemsim_lbm_restore(h: *mut chemsim_lbm_t, src: *const c_void, bytes: usize) -> c_int;
 
     pub fn chemsim_lbm_cuda_stream(h: *const chemsim_lbm_t, stream: *mut *mut c_void) -> c_int;
     pub fn chemsim_lbm_kernel_launches(h: *const chemsim_lbm_t, out: *mut u64) -> c_int;

@@ -1,13 +1,24 @@
-//! Drop-in for `chemsim::lbm` (reference: `src/lbm.rs`): the same public names, a device-resident
-//! lattice behind the C ABI.  UNCOMPILED in this repository (no Rust toolchain in the image).
+//! Drop-in for `chemsim::lbm` (reference: `src/lbm.rs`): the same public names and signatures, a
+//! device-resident lattice behind the C ABI.  UNCOMPILED in this repository (no Rust toolchain in the
+//! image); `chemsim_b200/cpp/lbm.hpp` is its compiled twin.
 //!
-//! What changes with respect to the reference, and why:
-//!  * `Populations` is an enum: the value of `compute_equilibrium` keeps its generating fields and
-//!    is evaluated on the GPU when the `State` is built, instead of nine arrays crossing the bus.
-//!  * `State` owns an opaque handle; `state.geometry` is an accessor object (`get` / `set`) because
-//!    the mask lives on the device (`src/main.rs:77-89` reads, edits and writes it back).
-//!  * `State::step` is ONE fused kernel (stream + bounce-back + collide); the three passes are not
-//!    separately callable.
+//! Kept exactly (so `src/main.rs` compiles against it after the one-line patch in rust/patches/):
+//!  * `Scalar`, `Vector`, `Discretization`, `Direction`, `Population = Matrix`,
+//!    `Populations = Vec<(Direction, Population)>`, `Geometry = af::Array<bool>` (the stand-in of
+//!    `af_compat`), `compute_equilibrium(..) -> Populations`, `D2Q9::new(&[Population])`,
+//!    `D2Q9::directions()`, `BGK { tau }`, `TRT::new`, `KBC::new`, `Regularized::new`,
+//!    `State::initial(Box<L>, Geometry, Box<CollisionOperator<L>>, Discretization)`, the public fields
+//!    `state.time` / `.lattice` / `.geometry` / `.collision` / `.discretization`, `State::step` and every
+//!    readout (`density`, `pressure`, `momentum_density`, `velocity`, `speed`, `populations`,
+//!    `equilibrium`, `non_equilibrium`, `is_unstable`, `size`, `delta_x`, `delta_t`).
+//! What differs, and why:
+//!  * `CollisionOperator::evaluate(&L, &Discretization) -> Populations` (`src/lbm.rs:328-333`) is replaced
+//!    by `apply` (select the operator on the device): collision is fused into the step kernel and is not
+//!    callable on its own.  Likewise `State::{stream, collide, bounce_back}` (:716-751) do not exist.
+//!  * `state.geometry` is a host value; `State::step` uploads it when it has been reassigned (main.rs:89).
+//!  * `Matrix` is a host `Vec<f32>` (no `get_array` / `unsafe_new`): `render.rs` is replaced by
+//!    `render::render_state` (device-side), see rust/patches/main_rs.patch.
+//!  * `state.lattice` keeps the populations it was BUILT from; the live ones are `state.populations()`.
 //!  * Errors: the reference panics on everything but `Matrix::new`; so does this shim (`check`).
 use std::ffi::CStr;
 use std::os::raw::c_int;
@@ -45,28 +56,13 @@ pub struct Direction { // src/lbm.rs:90-95
     pub stencil: [i8; 9],
 }
 
-/// Row-major `bool[y*w + x]`, what `main.rs:269-311` builds before uploading.
-pub type Geometry = Vec<bool>;
-pub type Population = Matrix;
+pub type Geometry = crate::af_compat::Array<bool>; // src/lbm.rs:99 (`af::Array<bool>`)
+pub type Population = Matrix;                      // src/lbm.rs:103
+pub type Populations = Vec<(Direction, Population)>; // src/lbm.rs:107
 
-/// `Vec<(Direction, Population)>` in the reference (`src/lbm.rs:107`).
-#[derive(Clone)]
-pub enum Populations {
-    Equilibrium { density: Matrix, velocity: (Matrix, Matrix), discretization: Discretization },
-    Explicit(Vec<(Direction, Population)>),
-}
-
-impl Populations {
-    pub fn len(&self) -> usize { 9 }
-    fn size(&self) -> (usize, usize) {
-        match self {
-            Populations::Equilibrium { density, .. } => density.get_shape(),
-            Populations::Explicit(p) => p[0].1.get_shape(),
-        }
-    }
-}
-
-/// `lbm::compute_equilibrium` (`src/lbm.rs:43-71`); evaluated on the device at `State::initial`.
+/// `lbm::compute_equilibrium` (`src/lbm.rs:43-71`), evaluated on the host in the reference's exact
+/// operation order (f32, no contraction): nine arrays, as in the reference.  It runs once, at set-up;
+/// `D2Q9::new` + `State::initial` upload them with `chemsim_lbm_set_population`.
 pub fn compute_equilibrium(
     density: Matrix,
     velocity: (Matrix, Matrix),
@@ -74,10 +70,26 @@ pub fn compute_equilibrium(
     discretization: Discretization,
 ) -> Populations {
     let size = density.get_shape();
-    assert_eq!(size, velocity.0.get_shape()); // src/lbm.rs:51
-    assert_eq!(size, velocity.1.get_shape()); // src/lbm.rs:52
-    assert_eq!(directions.len(), 9);
-    Populations::Equilibrium { density, velocity, discretization }
+    let (vx, vy) = velocity;
+    assert_eq!(size, vx.get_shape()); // src/lbm.rs:51
+    assert_eq!(size, vy.get_shape()); // src/lbm.rs:52
+    let v2 = vx.hadamard(&vx) + vy.hadamard(&vy);
+    let cs = discretization.isothermal_speed_of_sound();
+    let cs2 = cs * cs;
+    let cs4 = cs2 * cs2;
+    let mut result = Vec::with_capacity(directions.len());
+    for dir in directions {
+        let (cx, cy) = dir.c_vector.to_pair();
+        let vc = vx.scale(cx) + vy.scale(cy);
+        let vc2 = vc.hadamard(&vc);
+        let sum: Matrix = Matrix::new_filled(1.0, size)
+            + vc.scale(1.0 / cs2)
+            + vc2.scale(1.0 / (2.0 * cs4))
+            + v2.scale(-1.0 / (2.0 * cs2));
+        let pop = density.scale(dir.w_scalar).hadamard(&sum);
+        result.push((dir.clone(), pop));
+    }
+    result
 }
 
 pub trait Lattice { // src/lbm.rs:111-176 (the arithmetic methods moved onto State: they need the device)
@@ -92,22 +104,13 @@ pub struct D2Q9 { // src/lbm.rs:180-184
 }
 
 impl D2Q9 {
-    /// `D2Q9::new(&[Population; 9])` (`src/lbm.rs:187-200`), or the value of `compute_equilibrium`.
-    pub fn new(populations: Populations) -> Self {
+    /// `D2Q9::new(&[Population])` (`src/lbm.rs:187-200`).
+    pub fn new(populations: &[Population]) -> Self {
         assert!(populations.len() == 9);
-        if let Populations::Explicit(ref p) = populations {
-            assert!(p.len() == 9);
-            let size = p[0].1.get_shape();
-            for (_, pop) in p { assert_eq!(size, pop.get_shape()); }
-        }
-        D2Q9 { size: populations.size(), populations }
-    }
-
-    /// `D2Q9::new` from nine explicit arrays, in direction order.
-    pub fn from_arrays(populations: &[Population]) -> Self {
-        assert!(populations.len() == 9);
+        let size = populations[0].get_shape();
+        for pop in populations { assert_eq!(size, pop.get_shape()); }
         let dirs = Self::directions();
-        D2Q9::new(Populations::Explicit(dirs.iter().cloned().zip(populations.iter().cloned()).collect()))
+        D2Q9 { size, populations: dirs.iter().cloned().zip(populations.iter().cloned()).collect() }
     }
 
     /// `D2Q9::directions()` (`src/lbm.rs:202-282`).
@@ -136,7 +139,7 @@ impl Lattice for D2Q9 {
 
 pub trait CollisionOperator<L> {
     /// Select this operator on a device lattice (replaces `evaluate`, which ran on ArrayFire arrays).
-    fn apply(&self, handle: *mut ffi::chemsim_lbm_t) -> c_int;
+    fn apply(&self, handle: *mut ffi::chemsim_lbm_t, disc: &Discretization) -> c_int;
     fn kinematic_shear_viscosity(&self, disc: &Discretization) -> Scalar;
     #[inline(always)]
     fn kinematic_bulk_viscosity(&self, disc: &Discretization) -> Scalar {
@@ -147,7 +150,7 @@ pub trait CollisionOperator<L> {
 pub struct BGK { pub tau: Scalar } // src/lbm.rs:345-347
 
 impl<L: Lattice> CollisionOperator<L> for BGK {
-    fn apply(&self, h: *mut ffi::chemsim_lbm_t) -> c_int { unsafe { ffi::chemsim_lbm_set_bgk(h, self.tau as f64) } }
+    fn apply(&self, h: *mut ffi::chemsim_lbm_t, _d: &Discretization) -> c_int { unsafe { ffi::chemsim_lbm_set_bgk(h, self.tau as f64) } }
     fn kinematic_shear_viscosity(&self, disc: &Discretization) -> Scalar { // :366-369
         let (dx, dt) = (disc.delta_x, disc.delta_t);
         (dx * dx / (3.0 * dt * dt)) * (self.tau - dt / 2.0)
@@ -174,7 +177,7 @@ impl TRT {
 }
 
 impl<L: Lattice> CollisionOperator<L> for TRT {
-    fn apply(&self, h: *mut ffi::chemsim_lbm_t) -> c_int {
+    fn apply(&self, h: *mut ffi::chemsim_lbm_t, _d: &Discretization) -> c_int {
         unsafe { ffi::chemsim_lbm_set_trt(h, self.tau_plus as f64, self.tau_minus as f64) }
     }
     fn kinematic_shear_viscosity(&self, disc: &Discretization) -> Scalar { // :446-450
@@ -190,7 +193,7 @@ impl KBC {
 }
 
 impl CollisionOperator<D2Q9> for KBC {
-    fn apply(&self, h: *mut ffi::chemsim_lbm_t) -> c_int { unsafe { ffi::chemsim_lbm_set_kbc(h, self.ks_viscosity as f64) } }
+    fn apply(&self, h: *mut ffi::chemsim_lbm_t, _d: &Discretization) -> c_int { unsafe { ffi::chemsim_lbm_set_kbc(h, self.ks_viscosity as f64) } }
     fn kinematic_shear_viscosity(&self, _disc: &Discretization) -> Scalar { self.ks_viscosity } // :587-589
 }
 
@@ -202,9 +205,9 @@ impl<C> Regularized<C> {
 
 impl<L, C> CollisionOperator<L> for Regularized<C>
 where L: Lattice, C: CollisionOperator<L> {
-    fn apply(&self, h: *mut ffi::chemsim_lbm_t) -> c_int {
-        let unit = Discretization { delta_x: 1.0, delta_t: 1.0 };
-        unsafe { ffi::chemsim_lbm_set_regularized(h, self.underlying.kinematic_shear_viscosity(&unit) as f64) }
+    fn apply(&self, h: *mut ffi::chemsim_lbm_t, disc: &Discretization) -> c_int {
+        // only the underlying operator's viscosity is ever used (src/lbm.rs:663-665), with the State's discretization
+        unsafe { ffi::chemsim_lbm_set_regularized(h, self.underlying.kinematic_shear_viscosity(disc) as f64) }
     }
     fn kinematic_shear_viscosity(&self, disc: &Discretization) -> Scalar { // :663-665
         self.underlying.kinematic_shear_viscosity(disc)
@@ -220,43 +223,16 @@ fn check(status: c_int, h: *const ffi::chemsim_lbm_t) {
     }
 }
 
-/// Accessor for the device-resident geometry (`pub geometry: Geometry`, `src/lbm.rs:673`).
-pub struct GeometryHandle {
-    handle: *mut ffi::chemsim_lbm_t,
-    size: (usize, usize),
-}
-
-impl GeometryHandle {
-    pub fn dims(&self) -> (usize, usize) { self.size }
-    /// `geometry.host(&mut vec)`, `src/main.rs:81`.
-    pub fn get(&self) -> Geometry {
-        let n = self.size.0 * self.size.1;
-        let mut bytes = vec![0u8; n];
-        check(unsafe { ffi::chemsim_lbm_get_geometry(self.handle, bytes.as_mut_ptr(), n) }, self.handle);
-        bytes.into_iter().map(|b| b != 0).collect()
-    }
-    /// `self.state.geometry = af::Array::new(&vec[..], dims)`, `src/main.rs:89`.
-    pub fn set(&mut self, geometry: &[bool]) {
-        let bytes: Vec<u8> = geometry.iter().map(|&b| b as u8).collect();
-        check(unsafe { ffi::chemsim_lbm_set_geometry(self.handle, bytes.as_ptr(), bytes.len()) }, self.handle);
-    }
-    /// Rows `[row_begin, row_begin + rows)` only (a painted block touches a few rows).
-    pub fn set_rows(&mut self, row_begin: usize, geometry: &[bool]) {
-        let bytes: Vec<u8> = geometry.iter().map(|&b| b as u8).collect();
-        let rows = bytes.len() / self.size.0;
-        check(unsafe {
-            ffi::chemsim_lbm_set_geometry_rows(self.handle, row_begin as c_int, rows as c_int, bytes.as_ptr(), bytes.len())
-        }, self.handle);
-    }
-}
-
 pub struct State<L> {
     pub time: Scalar,
     pub lattice: Box<L>,
-    pub geometry: GeometryHandle,
+    /// Host value, as in the reference (`pub geometry: Geometry`, `src/lbm.rs:673`): read it with
+    /// `.dims()` / `.host()`, replace it by assignment (`src/main.rs:77-89`); `step` uploads a new one.
+    pub geometry: Geometry,
     pub collision: Box<dyn CollisionOperator<L>>,
     pub discretization: Discretization,
     handle: *mut ffi::chemsim_lbm_t,
+    uploaded_geometry: u64,
 }
 
 impl State<D2Q9> {
@@ -285,39 +261,49 @@ impl State<D2Q9> {
         check(unsafe {
             ffi::chemsim_lbm_set_discretization(handle, discretization.delta_x as f64, discretization.delta_t as f64)
         }, handle);
-        check(collision.apply(handle), handle);
-        match lattice.populations() {
-            Populations::Equilibrium { density, velocity, .. } => check(unsafe {
-                ffi::chemsim_lbm_init_equilibrium(
-                    handle,
-                    density.as_slice().as_ptr() as *const _,
-                    velocity.0.as_slice().as_ptr() as *const _,
-                    velocity.1.as_slice().as_ptr() as *const _,
-                    n,
-                )
-            }, handle),
-            Populations::Explicit(pops) => {
-                for (q, (_, pop)) in pops.iter().enumerate() {
-                    check(unsafe {
-                        ffi::chemsim_lbm_set_population(handle, q as c_int, pop.as_slice().as_ptr() as *const _, n)
-                    }, handle);
-                }
-            }
+        check(collision.apply(handle, &discretization), handle);
+        for (q, (_, pop)) in lattice.populations().iter().enumerate() {
+            check(unsafe {
+                ffi::chemsim_lbm_set_population(handle, q as c_int, pop.as_slice().as_ptr() as *const _, n)
+            }, handle);
         }
-        let mut state = State {
-            time: 0.0,
-            lattice,
-            geometry: GeometryHandle { handle, size: (w, h) },
-            collision,
-            discretization,
-            handle,
-        };
-        state.geometry.set(&geometry);
+        let mut state = State { time: 0.0, lattice, geometry, collision, discretization, handle, uploaded_geometry: 0 };
+        state.upload_geometry();
         state
+    }
+
+    /// The geometry array holds element (dim0 = y, dim1 = x) (`src/main.rs:308-311`: built with dims
+    /// [w, h] and transposed; the mouse handler builds it with the transposed dims directly, :77-89).
+    fn upload_geometry(&mut self) {
+        let (w, h) = self.size();
+        let dims = self.geometry.dims();
+        assert_eq!((dims[0] as usize, dims[1] as usize), (h, w));
+        let mut bytes = vec![0u8; w * h];
+        for y in 0..h { for x in 0..w { bytes[y * w + x] = self.geometry.at(y, x) as u8; } }
+        check(unsafe { ffi::chemsim_lbm_set_geometry(self.handle, bytes.as_ptr(), bytes.len()) }, self.handle);
+        self.uploaded_geometry = self.geometry.id();
+    }
+
+    /// The mouse handler of `src/main.rs:71-91` without its host round trip: the geometry becomes the
+    /// 9x9 block around the cursor, painted by two small kernels (`chemsim_lbm_fill_geometry` +
+    /// `chemsim_lbm_paint_rect`).  Optional: the unchanged handler (download, rewrite, assign) works too.
+    pub fn paint_brush(&mut self, pos: [f64; 2]) {
+        let (row, col) = (f64::floor(pos[1]) as i64, f64::floor(pos[0]) as i64);
+        let (w, h) = self.size();
+        if row < 0 || col < 0 || row as usize >= h || col as usize >= w { return; }
+        check(unsafe { ffi::chemsim_lbm_fill_geometry(self.handle, 0) }, self.handle);
+        check(unsafe { ffi::chemsim_lbm_paint_rect(self.handle, (col - 4) as c_int, (row - 4) as c_int, 9, 9, 1) }, self.handle);
+        let mut bits = vec![false; w * h];                     // keep the host value in step (column-major [h, w])
+        for y in 0..h { for x in 0..w {
+            bits[x * h + y] = (y as i64 - row).abs() < 5 && (x as i64 - col).abs() < 5;
+        } }
+        self.geometry = Geometry::new(&bits, crate::af_compat::Dim4::new(&[h as u64, w as u64, 1, 1]));
+        self.uploaded_geometry = self.geometry.id();
     }
 
     /// `State::step` (`src/lbm.rs:694-714`): stream -> bounce_back -> collide, one fused kernel.
     pub fn step(&mut self) {
+        if self.geometry.id() != self.uploaded_geometry { self.upload_geometry(); }   // `state.geometry = ...`
         check(unsafe { ffi::chemsim_lbm_step(self.handle, 1) }, self.handle);
         self.time += self.discretization.delta_t;
     }
@@ -352,7 +338,7 @@ impl State<D2Q9> {
     pub fn momentum_density(&self) -> (Matrix, Matrix) { self.read2(ffi::chemsim_lbm_get_momentum_density) } // :790
 
     fn read_q(&self, f: unsafe extern "C" fn(*mut ffi::chemsim_lbm_t, c_int, *mut std::os::raw::c_void, usize) -> c_int)
-        -> Vec<(Direction, Population)> {
+        -> Populations {
         let dirs = D2Q9::directions();
         (0..9).map(|q| {
             let mut m = Matrix::new_filled(0.0, self.size());
@@ -362,9 +348,9 @@ impl State<D2Q9> {
         }).collect()
     }
 
-    pub fn populations(&self) -> Vec<(Direction, Population)> { self.read_q(ffi::chemsim_lbm_get_population) }          // :769
-    pub fn equilibrium(&self) -> Vec<(Direction, Population)> { self.read_q(ffi::chemsim_lbm_get_equilibrium) }         // :805
-    pub fn non_equilibrium(&self) -> Vec<(Direction, Population)> { self.read_q(ffi::chemsim_lbm_get_non_equilibrium) } // :810
+    pub fn populations(&self) -> Populations { self.read_q(ffi::chemsim_lbm_get_population) }          // :769 (by value: device -> host)
+    pub fn equilibrium(&self) -> Populations { self.read_q(ffi::chemsim_lbm_get_equilibrium) }         // :805
+    pub fn non_equilibrium(&self) -> Populations { self.read_q(ffi::chemsim_lbm_get_non_equilibrium) } // :810
 
     pub fn is_unstable(&self) -> bool { // :815-818
         let mut flag: c_int = 0;
