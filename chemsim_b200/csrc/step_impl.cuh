@@ -401,9 +401,18 @@ static inline dim3 row_grid(int xchunks, int rowgroups)
     return dim3((unsigned)xchunks, (unsigned)gy, (unsigned)((rowgroups + gy - 1) / gy));
 }
 
+}  // namespace chemsim
+#ifdef CHEMSIM_EXPERIMENT_BULK
+#include "step_bulk_experiment.cuh"
+#endif
+namespace chemsim {
+
 template <typename T, int COL>
 void launch_step_col(const StepArgs<T> &a_in, cudaStream_t s)
 {
+#ifdef CHEMSIM_EXPERIMENT_BULK
+    if (launch_step_bulk_experiment<T, COL>(a_in, s)) return;      // A/B experiment build only
+#endif
     const int rows = a_in.y_count;
     if (use_vec(a_in)) {
         constexpr int V = VecOf<T>::N;

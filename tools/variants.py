@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": [],
+    "bulk": ["CHEMSIM_EXPERIMENT_BULK"],     # TMA bulk-copy loads (step_bulk_experiment.cuh); run with CHEMSIM_LBM_BULK=1 CHEMSIM_LBM_STEP2=0
     "mb5": ["CHEMSIM_STEP_MIN_BLOCKS=5"],
     "mb6": ["CHEMSIM_STEP_MIN_BLOCKS=6"],
     "t128": ["CHEMSIM_STEP_THREADS=128"],
@@ -24,7 +25,10 @@ VARIANTS = {
 
 if sys.argv[1] == "build":
     from chemsim_b200 import build
+    only = sys.argv[2:] or list(VARIANTS)
     for name, defs in VARIANTS.items():
+        if name not in only:
+            continue
         print(name, build.build_variant(name, defs))
 else:
     for name in VARIANTS:
