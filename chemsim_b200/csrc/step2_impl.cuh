@@ -134,17 +134,28 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
 #pragma unroll
                 for (int q = 0; q < Q; ++q) c[q] = T(0);
             } else {
+                // the three source rows / columns of this cell, wrapped once (not once per population):
+                // row[d], col[d] for a source at (gy + d - 1, gx + d - 1); population q reads (1 - ey_q, 1 - ex_q)
+                size_t row[3];
+                int col[3];
+                bool col_in[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    int sy = gy + d - 1, sx = gx + d - 1;
+                    if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
+                    // rows -GHOST .. H+GHOST-1 exist: ghost rows hold the neighbour slab's cells, or 0 at a zero-fill edge
+                    row[d] = (size_t)(sy + GHOST) * a.pitch;
+                    col_in[d] = true;
+                    if (PERIODIC_X) { if (sx < 0) sx = a.W - 1; else if (sx >= a.W) sx = 0; }
+                    else            { col_in[d] = sx >= 0 && sx < a.W; if (!col_in[d]) sx = gx; }
+                    col[d] = sx;
+                }
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    int sy = gy - ey_of(q), sx = gx - ex_of(q);
-                    bool in = true;
-                    if (a.wrap_y) { if (sy < 0) sy = a.H - 1; else if (sy >= a.H) sy = 0; }
-                    if (PERIODIC_X) { if (sx < 0) sx = a.W - 1; else if (sx >= a.W) sx = 0; }
-                    else            in = sx >= 0 && sx < a.W;
-                    // rows -GHOST .. H+GHOST-1 exist: ghost rows hold the neighbour slab's cells, or 0 at a zero-fill edge
-                    const T *cell = src + (size_t)q * a.plane + (size_t)(sy + GHOST) * a.pitch + sx;
+                    const T *cell = src + (size_t)q * a.plane + row[1 - ey_of(q)] + col[1 - ex_of(q)];
                     // ghost rows are written by the neighbouring GPU while this kernel may be resident: coherent load
-                    c[q] = in ? (P2P ? *reinterpret_cast<const volatile T *>(cell) : __ldg(cell)) : T(0);
+                    const T v = P2P ? *reinterpret_cast<const volatile T *>(cell) : __ldg(cell);
+                    c[q] = col_in[1 - ex_of(q)] ? v : T(0);
                 }
                 // gy may be -1 or H on a slab: the mask's halo row holds the neighbour's face row
                 if (use_mask) bounce_back(c, mask[(ptrdiff_t)gy * a.mask_pitch + gx] != 0);

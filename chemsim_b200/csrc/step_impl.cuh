@@ -112,7 +112,10 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
 template <typename T, int COL>
 constexpr int step_min_blocks()
 {
-    return COL == COL_KBC ? 1 : (COL != COL_BGK && sizeof(T) == 8 ? 3 : CHEMSIM_STEP_MIN_BLOCKS);
+#ifndef CHEMSIM_KBC_MIN_BLOCKS
+#define CHEMSIM_KBC_MIN_BLOCKS 1    // tools/variants.py: kbc3 / kbc4
+#endif
+    return COL == COL_KBC ? CHEMSIM_KBC_MIN_BLOCKS : (COL != COL_BGK && sizeof(T) == 8 ? 3 : CHEMSIM_STEP_MIN_BLOCKS);
 }
 
 // ---- the fused step, vector form ---------------------------------------------

@@ -13,6 +13,8 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": [],
     "bulk": ["CHEMSIM_EXPERIMENT_BULK"],     # TMA bulk-copy loads (step_bulk_experiment.cuh); run with CHEMSIM_LBM_BULK=1 CHEMSIM_LBM_STEP2=0
+    "kbc3": ["CHEMSIM_KBC_MIN_BLOCKS=3"],    # KBC capped at 80 registers (3 blocks/SM)
+    "kbc4": ["CHEMSIM_KBC_MIN_BLOCKS=4"],    # KBC capped at 64 registers (4 blocks/SM)
     "mb5": ["CHEMSIM_STEP_MIN_BLOCKS=5"],
     "mb6": ["CHEMSIM_STEP_MIN_BLOCKS=6"],
     "t128": ["CHEMSIM_STEP_THREADS=128"],
