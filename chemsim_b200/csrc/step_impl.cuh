@@ -473,7 +473,10 @@ step_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
         return;
     }
     const HaloP2P &p = a.halo;
-    const int halo_tok = order_after_halo_flags(p, r == 0, r == 2);    // rows 1 and H-2 read no ghost row
+    // Rows 0 / H-1 read a ghost row the neighbour writes; rows 1 / H-2 read none, but all four STORE into
+    // a neighbour's ghost rows of the buffer that neighbour's previous pass may still be reading: every face
+    // block waits for the flag of the neighbour it exchanges with (published = its face blocks are done).
+    const int halo_tok = order_after_halo_flags(p, r <= 1, r >= 2);
     step_vec_body<T, PERIODIC_X, HAS_MASK, COL, true>(a, y, xv, lane, halo_tok);
     __threadfence_system();
     __syncthreads();
