@@ -108,12 +108,14 @@ __device__ __forceinline__ unsigned ldg_mask(const uint8_t *p, bool pred, const 
 }
 
 // resident blocks per SM the step kernels are compiled for: BGK fits 64 registers in both
-// precisions; the f64 TRT / Regularized bodies need ~80 (3 blocks), KBC is left unconstrained
+// precisions; the f64 TRT / Regularized bodies need ~80 (3 blocks)
 template <typename T, int COL>
 constexpr int step_min_blocks()
 {
+    // KBC: f32 capped at 64 registers too (28 B of spill, +1.6 % measured: 58.2 vs 57.3 GLUPS); f64 left
+    // unconstrained (96 registers; the cap costs 6 %)
 #ifndef CHEMSIM_KBC_MIN_BLOCKS
-#define CHEMSIM_KBC_MIN_BLOCKS 1    // tools/variants.py: kbc3 / kbc4
+#define CHEMSIM_KBC_MIN_BLOCKS (sizeof(T) == 4 ? 4 : 1)    // tools/variants.py: kbc3 / kbc4 override
 #endif
     return COL == COL_KBC ? CHEMSIM_KBC_MIN_BLOCKS : (COL != COL_BGK && sizeof(T) == 8 ? 3 : CHEMSIM_STEP_MIN_BLOCKS);
 }
