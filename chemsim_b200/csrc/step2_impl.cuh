@@ -201,7 +201,7 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
 
 // rows [y_begin, y_begin + y_count) advance by two steps (unsharded lattice, or one region of a slab)
 template <typename T, bool PERIODIC_X, int COL, bool USE_MASK>
-__global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
+__global__ void __launch_bounds__(Step2Tile<T>::NT, Step2Tile<T>::BLOCKS)
 step2_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using TL = Step2Tile<T>;
@@ -217,7 +217,7 @@ step2_kernel(const __grid_constant__ StepArgs<T> a)
 // a whole y-slab, H >= 2 TY: tile-row slot 0 -> rows [0, TY), slot 1 -> rows [H-TY, H) (the two face
 // tile rows, dispatched first), slot s >= 2 -> rows [(s-1) TY, ...) clipped at H-TY
 template <typename T, bool PERIODIC_X, int COL, bool USE_MASK>
-__global__ void __launch_bounds__(Step2Tile<T>::NT, 2)
+__global__ void __launch_bounds__(Step2Tile<T>::NT, Step2Tile<T>::BLOCKS)
 step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using TL = Step2Tile<T>;

@@ -37,11 +37,16 @@ template <typename T>
 struct Step2Tile {
     static constexpr int V = VecOf<T>::N;          // cells per 16 bytes
     static constexpr int TX = 32 * V;              // one warp covers a tile row in phase B
-    static constexpr int TY = 16;
+#ifndef CHEMSIM_STEP2_TY
+#define CHEMSIM_STEP2_TY 16                        // tools/variants.py: s2ty8 / s2ty32 (measured: 16 is best)
+#endif
+    static constexpr int TY = CHEMSIM_STEP2_TY;
     static constexpr int NT = 32 * TY;             // threads per block: one warp per tile row
     static constexpr int EX = TX + 2, EY = TY + 2; // tile + one-cell rim
     static constexpr int SP = ((EX + V - 1 + V - 1) / V) * V;   // shared row pitch (room for the column shift)
     static constexpr size_t SMEM = (size_t)Q * EY * SP * sizeof(T);
+    // resident blocks per SM: shared memory (227 KB) and threads (2048) allow this many
+    static constexpr int BLOCKS = (int)((227u * 1024u) / SMEM) < 2048 / NT ? (int)((227u * 1024u) / SMEM) : 2048 / NT;
 };
 
 }  // namespace chemsim

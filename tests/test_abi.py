@@ -109,3 +109,28 @@ def test_missing_extension_fails_loudly(tmp_path):
             % (ROOT, str(tmp_path / "nope.so")))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert "LOUD True" in res.stdout, res.stdout + res.stderr
+
+
+def test_rust_binding_declares_every_symbol_of_the_header():
+    """rust/src/ffi.rs cannot be compiled here (no rustc), so at least hold it to the header textually:
+    every entry point is declared, and nothing is declared that the header does not have."""
+    text = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (chemsim_lbm_[a-z0-9_]+)\s*\(", text)))
+    assert declared == declared_symbols()
+
+
+def test_rust_shim_keeps_the_reference_signatures():
+    """The items of lbm.rs's public surface that main.rs touches, as text."""
+    text = open(os.path.join(ROOT, "rust", "src", "lbm.rs")).read()
+    for needle in ("pub type Scalar = f32;", "pub type Populations = Vec<(Direction, Population)>;",
+                   "pub type Geometry = crate::af_compat::Array<bool>;",
+                   "pub fn new(populations: &[Population]) -> Self",
+                   "pub fn directions() -> [Direction; 9]", "pub struct BGK { pub tau: Scalar }",
+                   "pub fn new(lambda: Scalar, ks_viscosity: Scalar, disc: &Discretization) -> Self",
+                   "pub geometry: Geometry,", "pub time: Scalar,", "pub fn step(&mut self)",
+                   "pub fn density(&self) -> Matrix", "pub fn velocity(&self) -> (Matrix, Matrix)",
+                   "pub fn momentum_density(&self) -> (Matrix, Matrix)", "pub fn speed(&self) -> Matrix",
+                   "pub fn is_unstable(&self) -> bool"):
+        assert needle in text, needle
+    patch = open(os.path.join(ROOT, "rust", "patches", "main_rs.patch")).read()
+    assert patch.count("\n@@") == 2 and "use chemsim::af_compat as af;" in patch
