@@ -37,8 +37,11 @@ template <typename T>
 struct Step2Tile {
     static constexpr int V = VecOf<T>::N;          // cells per 16 bytes
     static constexpr int TX = 32 * V;              // one warp covers a tile row in phase B
+    // tile height (tools/variants.py s2ty8 / s2ty32 override it).  Measured on 4096^2 BGK, GLUPS f32 / f64:
+    // TY = 8: 125.9 / 69.6, TY = 16: 124.7 / 66.2, TY = 32: 115.7 / 58.9 (one block per SM: the phases of
+    // different blocks no longer overlap).  f32 is power-capped either way (TY = 8 runs at lower clocks).
 #ifndef CHEMSIM_STEP2_TY
-#define CHEMSIM_STEP2_TY 16                        // tools/variants.py: s2ty8 / s2ty32 (measured: 16 is best)
+#define CHEMSIM_STEP2_TY (sizeof(T) == 8 ? 8 : 16)
 #endif
     static constexpr int TY = CHEMSIM_STEP2_TY;
     static constexpr int NT = 32 * TY;             // threads per block: one warp per tile row
