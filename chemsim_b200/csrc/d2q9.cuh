@@ -69,6 +69,43 @@ __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, 
 __device__ __forceinline__ double divi(double a, double b){ return __ddiv_rn(a, b); }
 __device__ __forceinline__ double root(double a)          { return __dsqrt_rn(a); }
 
+// ---- two f32 cells per thread in one register pair (sm_100a packed FP32) ----------------------
+// Blackwell issues add.rn.f32x2 (SASS FADD2) as ONE instruction for two IEEE round-to-nearest
+// additions, lane by lane bit-identical to two scalar FADDs.  The f32 step kernels are bound by
+// instruction issue, not by the FP32 pipe, so they run the collision of two cells at once on
+// values of this type: every addition/subtraction is one packed instruction.  The
+// MULTIPLICATIONS stay scalar on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+// even with explicit .rn and --fmad=false (seen in SASS, CUDA 12.9), which would change the
+// rounding; a scalar mul.rn.f32 feeding a packed add is never contracted.  tools/sass_count.py
+// --no-ffma2 checks that the built kernels contain no FFMA2 at all.
+struct F32x2 {
+    float lo, hi;
+    F32x2() = default;
+    __device__ __forceinline__ F32x2(float x) : lo(x), hi(x) {}
+    __device__ __forceinline__ F32x2(float l, float h) : lo(l), hi(h) {}
+};
+#if defined(__CUDACC__)
+#define CHEMSIM_F32X2_OP(NAME, PTX, HOSTOP)                                                           \
+    __device__ __forceinline__ F32x2 NAME(F32x2 a, F32x2 b)                                           \
+    {                                                                                                 \
+        F32x2 r;                                                                                      \
+        asm("{\n\t.reg .b64 pa, pb, pr;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\t"       \
+            PTX ".rn.f32x2 pr, pa, pb;\n\tmov.b64 {%0, %1}, pr;\n\t}"                                 \
+            : "=f"(r.lo), "=f"(r.hi) : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi));                   \
+        return r;                                                                                     \
+    }
+#else   // tests/host_arith: the same two IEEE operations, lane by lane
+#define CHEMSIM_F32X2_OP(NAME, PTX, HOSTOP)                                                           \
+    inline F32x2 NAME(F32x2 a, F32x2 b) { return F32x2(HOSTOP(a.lo, b.lo), HOSTOP(a.hi, b.hi)); }
+#endif
+CHEMSIM_F32X2_OP(add, "add", __fadd_rn)
+CHEMSIM_F32X2_OP(sub, "sub", __fsub_rn)
+#undef CHEMSIM_F32X2_OP
+__device__ __forceinline__ F32x2 mul(F32x2 a, F32x2 b)  { return F32x2(__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)); }
+__device__ __forceinline__ F32x2 divi(F32x2 a, F32x2 b) { return F32x2(__fdiv_rn(a.lo, b.lo), __fdiv_rn(a.hi, b.hi)); }
+__device__ __forceinline__ F32x2 root(F32x2 a)          { return F32x2(__fsqrt_rn(a.lo), __fsqrt_rn(a.hi)); }
+__device__ __forceinline__ F32x2 recip(F32x2 a)         { return F32x2(__frcp_rn(a.lo), __frcp_rn(a.hi)); }
+
 // Macroscopic moments of one cell, in the reference's order.
 template <typename T>
 struct Moments { T rho, mx, my, vx, vy; };
@@ -157,8 +194,8 @@ __device__ __forceinline__ Moments<T> moments_reduced(const T (&g)[Q])
 }
 
 // compute_equilibrium for all nine directions (src/lbm.rs:58-68) by identities (1), (3), (4).
-template <typename T>
-__device__ __forceinline__ void equilibrium_pair(T vc, T c, T rw, const Consts<T> &k, T &fe_i, T &fe_opp)
+template <typename T, typename K>
+__device__ __forceinline__ void equilibrium_pair(T vc, T c, T rw, const K &k, T &fe_i, T &fe_opp)
 {
     const T a = mul(vc, k.k1);
     const T b = mul(mul(vc, vc), k.k2);
@@ -166,8 +203,8 @@ __device__ __forceinline__ void equilibrium_pair(T vc, T c, T rw, const Consts<T
     fe_opp = mul(rw, add(add(sub(T(1), a), b), c));     // vc_opp = -vc: 1 + (-a) == 1 - a
 }
 
-template <typename T>
-__device__ __forceinline__ void equilibrium_all(const T (&g)[Q], const Consts<T> &k, Moments<T> &m, T (&fe)[Q])
+template <typename T, typename K>
+__device__ __forceinline__ void equilibrium_all(const T (&g)[Q], const K &k, Moments<T> &m, T (&fe)[Q])
 {
     m = moments_reduced(g);
     const T v2 = add(mul(m.vx, m.vx), mul(m.vy, m.vy));   // src/lbm.rs:53
@@ -181,8 +218,8 @@ __device__ __forceinline__ void equilibrium_all(const T (&g)[Q], const Consts<T>
 }
 
 // State::collide with BGK (src/lbm.rs:731-739, :349-364): g <- g + (g - feq)*factor
-template <typename T>
-__device__ __forceinline__ void collide_bgk(T (&g)[Q], const Consts<T> &k)
+template <typename T, typename K>
+__device__ __forceinline__ void collide_bgk(T (&g)[Q], const K &k)
 {
     Moments<T> m; T fe[Q];
     equilibrium_all(g, k, m, fe);
@@ -205,8 +242,8 @@ struct Num {
 
 // TRT::evaluate (src/lbm.rs:401-444).  swap_equilibrium (:311-322) overwrites slots
 // 1..8 of the equilibrium with the opposite *population* — reproduced as written.
-template <typename T>
-__device__ __forceinline__ void collide_trt(T (&g)[Q], const Consts<T> &k)
+template <typename T, typename K>
+__device__ __forceinline__ void collide_trt(T (&g)[Q], const K &k)
 {
     using N = Num<T>;
     Moments<T> m; T fe[Q];
@@ -228,8 +265,8 @@ __device__ __forceinline__ void collide_trt(T (&g)[Q], const Consts<T> &k)
 // yx sum repeats the xy sum operand for operand.  The second loop (:647-658) shares its products
 // between directions of equal (c^2, w) (identity (4): axx_1 == axx_3, axx_5..8 equal, axy_6 ==
 // -axy_5, ...) and skips the +-0 terms of the axis directions.
-template <typename T>
-__device__ __forceinline__ void collide_regularized(T (&g)[Q], const Consts<T> &k)
+template <typename T, typename K>
+__device__ __forceinline__ void collide_regularized(T (&g)[Q], const K &k)
 {
     Moments<T> m; T fe[Q];
     equilibrium_all(g, k, m, fe);
@@ -254,8 +291,8 @@ __device__ __forceinline__ void collide_regularized(T (&g)[Q], const Consts<T> &
 }
 
 // KBC::evaluate (src/lbm.rs:468-585), entropic stabiliser gamma*.
-template <typename T>
-__device__ __forceinline__ void collide_kbc(T (&g)[Q], const Consts<T> &k)
+template <typename T, typename K>
+__device__ __forceinline__ void collide_kbc(T (&g)[Q], const K &k)
 {
     using N = Num<T>;
     Moments<T> m; T fe[Q];
@@ -292,13 +329,30 @@ __device__ __forceinline__ void collide_kbc(T (&g)[Q], const Consts<T> &k)
 // State::collide (src/lbm.rs:731-739): dispatch on the operator; COL is a
 // template parameter of the step kernels (the reference dispatches dynamically
 // through Box<dyn CollisionOperator>, :674).
-template <int COL, typename T>
-__device__ __forceinline__ void collide(T (&g)[Q], const Consts<T> &k)
+template <int COL, typename T, typename K>
+__device__ __forceinline__ void collide(T (&g)[Q], const K &k)
 {
     if (COL == COL_BGK) collide_bgk(g, k);
     else if (COL == COL_TRT) collide_trt(g, k);
     else if (COL == COL_REGULARIZED) collide_regularized(g, k);
     else collide_kbc(g, k);
+}
+
+// Two cells at once.  PACK (f32 only): the packed form above; otherwise one after the other.
+template <int COL, bool PACK, typename T, typename K>
+__device__ __forceinline__ void collide2(T (&c0)[Q], T (&c1)[Q], const K &k)
+{
+    if constexpr (PACK && sizeof(T) == 4) {
+        F32x2 p[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) p[q] = F32x2(c0[q], c1[q]);
+        collide<COL>(p, k);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { c0[q] = p[q].lo; c1[q] = p[q].hi; }
+    } else {
+        collide<COL>(c0, k);
+        collide<COL>(c1, k);
+    }
 }
 
 // State::bounce_back (src/lbm.rs:741-751): g_i <- solid ? g_opp(i) : g_i

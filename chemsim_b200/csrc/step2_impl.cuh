@@ -86,12 +86,11 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
                     bounce_back(c0, s0);
                     bounce_back(c1, s1);
                 }
-                collide<COL>(c0, a.k);
+                collide2<COL, CHEMSIM_PACKED_STEP2 != 0>(c0, c1, a.k);              // without a second cell c1 repeats c0 (discarded)
                 T *d0 = sm + ey0 * SP + ex0;
 #pragma unroll
                 for (int q = 0; q < Q; ++q) d0[q * (EY * SP) + shift_of<V>(q)] = c0[q];
                 if (two) {
-                    collide<COL>(c1, a.k);
                     T *d1 = sm + ey1 * SP + ex1;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) d1[q * (EY * SP) + shift_of<V>(q)] = c1[q];
@@ -184,14 +183,17 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
     unsigned maskw = 0;
     if (use_mask) maskw = ldg_mask(mask + (size_t)gy * a.mask_pitch + gx0, true, (const T *)nullptr);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        T c[Q];
+    for (int j = 0; j < V; j += 2) {
+        T c0[Q], c1[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) c[q] = g[q][j];
-        if (use_mask) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
-        collide<COL>(c, a.k);
+        for (int q = 0; q < Q; ++q) { c0[q] = g[q][j]; c1[q] = g[q][j + 1]; }
+        if (use_mask) {
+            bounce_back(c0, ((maskw >> (8 * j)) & 0xffu) != 0);
+            bounce_back(c1, ((maskw >> (8 * j + 8)) & 0xffu) != 0);
+        }
+        collide2<COL, CHEMSIM_PACKED_STEP2 != 0>(c0, c1, a.k);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) g[q][j] = c[q];
+        for (int q = 0; q < Q; ++q) { g[q][j] = c0[q]; g[q][j + 1] = c1[q]; }
     }
     char *out = reinterpret_cast<char *>(a.dst) + ((size_t)(gy + GHOST) * a.pitch + gx0) * sizeof(T);
 #pragma unroll

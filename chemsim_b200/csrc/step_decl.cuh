@@ -20,6 +20,17 @@ template <> struct VecOf<double> { using type = double2; static constexpr int N 
 #define CHEMSIM_STEP_MIN_BLOCKS 4   // <= 64 registers: 4 x 256 threads per SM (ptxas otherwise takes 88 for f64)
 #endif
 constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
+// f32: collide two cells at once with packed additions (F32x2, d2q9.cuh).  The two-step kernels
+// always have two cells per thread in flight, so it costs them no registers; the single-step
+// vector kernels are capped at 64 registers and would spill, and BGK is HBM-bound there anyway:
+// a bit mask over the Collision enum says which operators' single-step kernels pack.
+#ifndef CHEMSIM_PACKED_STEP2
+#define CHEMSIM_PACKED_STEP2 1
+#endif
+#ifndef CHEMSIM_PACKED_VEC
+#define CHEMSIM_PACKED_VEC 0
+#endif
+template <int COL> __host__ __device__ constexpr bool vec_packed() { return ((CHEMSIM_PACKED_VEC >> COL) & 1) != 0; }
 
 // widths that are a multiple of the vector width take the 128-bit kernels
 template <typename T>

@@ -237,16 +237,19 @@ __device__ __forceinline__ void step_vec_body(const StepArgs<T> &a, const int y,
     }
     if (!active) return;
 
-    // ---- phase 3: bounce-back + collide, cell by cell ---------------------------
+    // ---- phase 3: bounce-back + collide, two cells at a time (f32: packed adds) ---
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        T c[Q];
+    for (int j = 0; j < V; j += 2) {
+        T c0[Q], c1[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) c[q] = g[q][j];
-        if (HAS_MASK) bounce_back(c, ((maskw >> (8 * j)) & 0xffu) != 0);
-        collide<COL>(c, a.k);
+        for (int q = 0; q < Q; ++q) { c0[q] = g[q][j]; c1[q] = g[q][j + 1]; }
+        if (HAS_MASK) {
+            bounce_back(c0, ((maskw >> (8 * j)) & 0xffu) != 0);
+            bounce_back(c1, ((maskw >> (8 * j + 8)) & 0xffu) != 0);
+        }
+        collide2<COL, vec_packed<COL>()>(c0, c1, a.k);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) g[q][j] = c[q];
+        for (int q = 0; q < Q; ++q) { g[q][j] = c0[q]; g[q][j + 1] = c1[q]; }
     }
 
     // ---- phase 4: nine aligned vector stores ------------------------------------

@@ -27,26 +27,44 @@ static inline double __drcp_rn(double a)           { return 1.0 / a; }
 
 using namespace chemsim;
 
-template <typename T, int COL>
+template <typename T>
+static void pull_cell(const T *src, const uint8_t *solid, int W, int H, int periodic, int y, int x, T (&c)[Q])
+{
+    const size_t plane = (size_t)W * H;
+    for (int q = 0; q < Q; ++q) {
+        int sy = y - ey_of(q), sx = x - ex_of(q);
+        bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
+        if (!inside && periodic) { sy = (sy + H) % H; sx = (sx + W) % W; inside = true; }
+        c[q] = inside ? src[q * plane + (size_t)sy * W + sx] : T(0);
+    }
+    bounce_back(c, solid && solid[(size_t)y * W + x] != 0);
+}
+
+// PAIRS: two neighbouring cells at a time through collide2<COL, true> — for f32 the F32x2
+// instantiation of the collision operators that the f32 step kernels run (its packed additions
+// are two lane-wise IEEE additions here, see d2q9.cuh)
+template <typename T, int COL, bool PAIRS>
 static void step_col(const T *src, T *dst, const uint8_t *solid, int W, int H, int periodic, const Consts<T> &k)
 {
     const size_t plane = (size_t)W * H;
     for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
+        for (int x = 0; x < W; x += PAIRS ? 2 : 1) {
             T c[Q];
-            for (int q = 0; q < Q; ++q) {
-                int sy = y - ey_of(q), sx = x - ex_of(q);
-                bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
-                if (!inside && periodic) { sy = (sy + H) % H; sx = (sx + W) % W; inside = true; }
-                c[q] = inside ? src[q * plane + (size_t)sy * W + sx] : T(0);
+            pull_cell(src, solid, W, H, periodic, y, x, c);
+            if (PAIRS) {
+                const int x1 = x + 1 < W ? x + 1 : x;      // odd width: the last cell is paired with itself
+                T d[Q];
+                pull_cell(src, solid, W, H, periodic, y, x1, d);
+                collide2<COL, true>(c, d, k);
+                for (int q = 0; q < Q; ++q) dst[q * plane + (size_t)y * W + x1] = d[q];
+            } else {
+                collide<COL>(c, k);
             }
-            bounce_back(c, solid && solid[(size_t)y * W + x] != 0);
-            collide<COL>(c, k);
             for (int q = 0; q < Q; ++q) dst[q * plane + (size_t)y * W + x] = c[q];
         }
 }
 
-template <typename T>
+template <typename T, bool PAIRS>
 static int step_any(const T *src, T *dst, const uint8_t *solid, int W, int H, int periodic, double dx, double dt,
                     int kind, double tau, double tau_plus, double tau_minus, double viscosity)
 {
@@ -54,10 +72,10 @@ static int step_any(const T *src, T *dst, const uint8_t *solid, int W, int H, in
     c.kind = kind; c.tau = tau; c.tau_plus = tau_plus; c.tau_minus = tau_minus; c.viscosity = viscosity;
     const Consts<T> k = make_consts<T>(dx, dt, c);
     switch (kind) {
-    case COL_BGK:         step_col<T, COL_BGK>(src, dst, solid, W, H, periodic, k); return 0;
-    case COL_TRT:         step_col<T, COL_TRT>(src, dst, solid, W, H, periodic, k); return 0;
-    case COL_REGULARIZED: step_col<T, COL_REGULARIZED>(src, dst, solid, W, H, periodic, k); return 0;
-    case COL_KBC:         step_col<T, COL_KBC>(src, dst, solid, W, H, periodic, k); return 0;
+    case COL_BGK:         step_col<T, COL_BGK, PAIRS>(src, dst, solid, W, H, periodic, k); return 0;
+    case COL_TRT:         step_col<T, COL_TRT, PAIRS>(src, dst, solid, W, H, periodic, k); return 0;
+    case COL_REGULARIZED: step_col<T, COL_REGULARIZED, PAIRS>(src, dst, solid, W, H, periodic, k); return 0;
+    case COL_KBC:         step_col<T, COL_KBC, PAIRS>(src, dst, solid, W, H, periodic, k); return 0;
     }
     return 1;
 }
@@ -66,11 +84,17 @@ extern "C" {
 int host_step_f32(const float *src, float *dst, const uint8_t *solid, int W, int H, int periodic, double dx, double dt,
                   int kind, double tau, double tau_plus, double tau_minus, double viscosity)
 {
-    return step_any<float>(src, dst, solid, W, H, periodic, dx, dt, kind, tau, tau_plus, tau_minus, viscosity);
+    return step_any<float, false>(src, dst, solid, W, H, periodic, dx, dt, kind, tau, tau_plus, tau_minus, viscosity);
+}
+// the F32x2 ("packed") instantiation, two cells at a time
+int host_step_f32_pairs(const float *src, float *dst, const uint8_t *solid, int W, int H, int periodic, double dx,
+                        double dt, int kind, double tau, double tau_plus, double tau_minus, double viscosity)
+{
+    return step_any<float, true>(src, dst, solid, W, H, periodic, dx, dt, kind, tau, tau_plus, tau_minus, viscosity);
 }
 int host_step_f64(const double *src, double *dst, const uint8_t *solid, int W, int H, int periodic, double dx, double dt,
                   int kind, double tau, double tau_plus, double tau_minus, double viscosity)
 {
-    return step_any<double>(src, dst, solid, W, H, periodic, dx, dt, kind, tau, tau_plus, tau_minus, viscosity);
+    return step_any<double, false>(src, dst, solid, W, H, periodic, dx, dt, kind, tau, tau_plus, tau_minus, viscosity);
 }
 }

@@ -134,3 +134,34 @@ def test_rust_shim_keeps_the_reference_signatures():
         assert needle in text, needle
     patch = open(os.path.join(ROOT, "rust", "patches", "main_rs.patch")).read()
     assert patch.count("\n@@") == 2 and "use chemsim::af_compat as af;" in patch
+
+
+def test_packed_f32_additions_are_never_contracted(lib):
+    """The f32 two-step kernels collide two cells at once with packed additions (SASS FADD2, d2q9.cuh
+    F32x2).  ptxas contracts a packed multiplication feeding a packed addition into FFMA2 even under
+    --fmad=false, which would change the rounding — so the library must contain packed ADDITIONS only:
+    no FFMA2, no FMUL2, and FADD2 in every f32 two-step kernel."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _ffi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    counts, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            counts[fn] = {"FADD2": 0, "FFMA2": 0, "FMUL2": 0}
+            continue
+        if fn:
+            for op in ("FADD2", "FFMA2", "FMUL2"):
+                if re.search(r"\b%s\b" % op, line):
+                    counts[fn][op] += 1
+    assert counts
+    assert all(c["FFMA2"] == 0 and c["FMUL2"] == 0 for c in counts.values())
+    step2_f32 = [c for name, c in counts.items() if re.search(r"step2_(slab_p2p_)?kernelIf", name)]
+    assert len(step2_f32) >= 12                      # 3 operators x (periodic, mask) variants, plain and peer-memory
+    assert all(c["FADD2"] > 100 for c in step2_f32)
+    step2_f64 = [c for name, c in counts.items() if re.search(r"step2_(slab_p2p_)?kernelId", name)]
+    assert step2_f64 and all(c["FADD2"] == 0 for c in step2_f64)

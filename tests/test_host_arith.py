@@ -32,11 +32,14 @@ def host():
     return C.CDLL(lib)
 
 
-def host_step(lib, f, solid, nsteps, col, edge, dx=1.0, dt=1.0):
+def host_step(lib, f, solid, nsteps, col, edge, dx=1.0, dt=1.0, pairs=False):
     a = np.array(f, order="C", copy=True)
     b = np.empty_like(a)
     _, h, w = a.shape
     fn = lib.host_step_f32 if a.dtype == np.float32 else lib.host_step_f64
+    if pairs:                                     # collide2<COL, true>: the F32x2 instantiation of the operators
+        assert a.dtype == np.float32
+        fn = lib.host_step_f32_pairs
     sp = None
     if solid is not None:
         solid = np.ascontiguousarray(solid, dtype=np.uint8)
@@ -77,6 +80,33 @@ def test_product_arithmetic_is_bit_identical_to_the_literal_oracle(host, name, e
         got = host_step(host, f0, solid, 4, col, edge)
         assert np.isfinite(ref).all()
         np.testing.assert_array_equal(bits(got), bits(ref), err_msg=f"{name} {w}x{h}")
+
+
+@pytest.mark.parametrize("edge", [O.EDGE_ZEROFILL, O.EDGE_PERIODIC])
+@pytest.mark.parametrize("name", sorted(COLLISIONS))
+def test_two_cell_f32_instantiation_is_bit_identical_too(host, name, edge):
+    """The f32 step kernels collide two cells at once on F32x2 values (packed additions, d2q9.cuh):
+    the same templates instantiated for that type must evaluate the very same expression tree —
+    every overload resolving to the f32 operation, every constant broadcast in f32."""
+    col = COLLISIONS[name]
+    for (w, h, seed) in ((40, 24, 1), (37, 9, 2), (5, 3, 3)):
+        rho, vx, vy, solid = scenarios.random_state(w, h, np.float32, seed=seed)
+        f0 = O.compute_equilibrium(rho, vx, vy)
+        f0 = (f0 * (1.0 + 0.2 * (np.random.default_rng(seed).random(f0.shape) - 0.5))).astype(np.float32)
+        ref = O.step_ref(f0, solid, 4, col, edge)
+        got = host_step(host, f0, solid, 4, col, edge, pairs=True)
+        np.testing.assert_array_equal(bits(got), bits(ref), err_msg=f"{name} {w}x{h}")
+    # signed zeros and exact zeros (fluid at rest, zero-fill edges)
+    rho = np.ones((10, 24), np.float32)
+    z = np.zeros((10, 24), np.float32)
+    solid = np.zeros((10, 24), np.uint8)
+    solid[4:6, 7:9] = 1
+    f0 = O.compute_equilibrium(rho, z, -z)
+    ref = O.step_ref(f0, solid, 5, col, edge)
+    got = host_step(host, f0, solid, 5, col, edge, pairs=True)
+    ok = ~np.isnan(ref)
+    assert (np.isnan(ref) == np.isnan(got)).all()
+    np.testing.assert_array_equal(bits(got)[ok], bits(ref)[ok], err_msg=name)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -15,6 +15,10 @@ VARIANTS = {
     "bulk": ["CHEMSIM_EXPERIMENT_BULK"],     # TMA bulk-copy loads (step_bulk_experiment.cuh); run with CHEMSIM_LBM_BULK=1 CHEMSIM_LBM_STEP2=0
     "s2ty8": ["CHEMSIM_STEP2_TY=8"],         # two-step kernel: 8-row tiles (256 threads, 4 blocks/SM, rim +27 %)
     "s2ty32": ["CHEMSIM_STEP2_TY=32"],       # 32-row tiles (1024 threads, 1 block/SM, rim +8 %)
+    "scalar": ["CHEMSIM_PACKED_STEP2=0"],    # two-step kernels without the packed f32 additions (the r02 build before F32x2)
+    "vp": ["CHEMSIM_PACKED_VEC=0x1e"],       # single-step vector kernels packed too, 64-register cap (spills)
+    "vp3": ["CHEMSIM_PACKED_VEC=0x1e", "CHEMSIM_STEP_MIN_BLOCKS=3", "CHEMSIM_KBC_MIN_BLOCKS=3"],   # ... at 80 registers
+    "vp2": ["CHEMSIM_PACKED_VEC=0x1e", "CHEMSIM_STEP_MIN_BLOCKS=2", "CHEMSIM_KBC_MIN_BLOCKS=2"],   # ... at 128 registers
     "kbc3": ["CHEMSIM_KBC_MIN_BLOCKS=3"],    # KBC capped at 80 registers (3 blocks/SM)
     "kbc4": ["CHEMSIM_KBC_MIN_BLOCKS=4"],    # KBC capped at 64 registers (4 blocks/SM)
     "mb5": ["CHEMSIM_STEP_MIN_BLOCKS=5"],
