@@ -101,7 +101,27 @@ struct F32x2 {
 CHEMSIM_F32X2_OP(add, "add", __fadd_rn)
 CHEMSIM_F32X2_OP(sub, "sub", __fsub_rn)
 #undef CHEMSIM_F32X2_OP
+// -DCHEMSIM_PACKED_MUL=1: packed multiplications after all, written as fma.rn.f32x2(a, b, -0) with the
+// -0 read from constant memory, i.e. opaque to ptxas.  RN(a*b + (-0)) == RN(a*b) for every a, b
+// (a zero product keeps its sign: (+0) + (-0) = +0, (-0) + (-0) = -0; inf*0 stays NaN), and an FMA
+// cannot be contracted any further with the addition that consumes it.
+#ifndef CHEMSIM_PACKED_MUL
+#define CHEMSIM_PACKED_MUL 0
+#endif
+#if defined(__CUDACC__) && CHEMSIM_PACKED_MUL
+static __constant__ float chemsim_neg_zero = -0.0f;
+__device__ __forceinline__ F32x2 mul(F32x2 a, F32x2 b)
+{
+    F32x2 r;
+    const float nz = chemsim_neg_zero;
+    asm("{\n\t.reg .b64 pa, pb, pc, pr;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tmov.b64 pc, {%6, %6};\n\t"
+        "fma.rn.f32x2 pr, pa, pb, pc;\n\tmov.b64 {%0, %1}, pr;\n\t}"
+        : "=f"(r.lo), "=f"(r.hi) : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi), "f"(nz));
+    return r;
+}
+#else
 __device__ __forceinline__ F32x2 mul(F32x2 a, F32x2 b)  { return F32x2(__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)); }
+#endif
 __device__ __forceinline__ F32x2 divi(F32x2 a, F32x2 b) { return F32x2(__fdiv_rn(a.lo, b.lo), __fdiv_rn(a.hi, b.hi)); }
 __device__ __forceinline__ F32x2 root(F32x2 a)          { return F32x2(__fsqrt_rn(a.lo), __fsqrt_rn(a.hi)); }
 __device__ __forceinline__ F32x2 recip(F32x2 a)         { return F32x2(__frcp_rn(a.lo), __frcp_rn(a.hi)); }

@@ -63,6 +63,9 @@ struct StepArgs {
     long long ld_off[Q];   // (q*plane - ey_q*pitch) * sizeof(T)
     long long st_off[Q];   // q*plane * sizeof(T)
     long long wrap_bytes;  // H*pitch*sizeof(T): what wrap_y adds/subtracts for the rows 0 / H-1
+    int prefetch_tiles;    // two-step kernels: every block asks L2 for the source lines of the tile this many
+                           // tiles further down the dispatch order (set by the launcher, 0 = off) ...
+    int prefetch_rows, prefetch_cols;   // ... = prefetch_rows tile rows + prefetch_cols tile columns (no division on the device)
     HaloP2P halo;
     Consts<T> k;
 

@@ -178,6 +178,7 @@ StepArgs<T> step_args(const chemsim_lbm *h, int y_begin, int y_count, int y_stri
     a.collision = h->col.kind;
     a.mask_flags = h->mask_flags;
     a.flag_pitch = h->flag_pitch;
+    a.prefetch_tiles = a.prefetch_rows = a.prefetch_cols = 0;   // set by the two-step launchers
     a.k = consts_of<T>(h);
     a.fill_offsets();
     return a;

@@ -36,6 +36,26 @@ namespace {
 // column shift of population q in shared memory: makes (x + 1 - ex_q + shift_q) a multiple of V
 template <int V> __host__ __device__ constexpr int shift_of(int q) { return (((ex_of(q) - 1) % V) + V) % V; }
 
+// L2 prefetch of a LATER tile's source lines (a hint, no effect on results).  A block lives for one
+// "wave" (~10 us at 4096^2); its first loads would otherwise wait for HBM.  The tile that the block
+// `prefetch_tiles` further down the dispatch order will work on is requested into L2 now, so that
+// those loads find it there (the working set of one wave, ~26 MB, is far below the 126 MB L2).
+// Only full tiles strictly inside the lattice / slab (rows pty0-1 .. pty0+TY all own rows) are
+// requested: nothing outside the buffers, no ghost row.
+template <typename T>
+__device__ __forceinline__ void step2_prefetch_tile(const StepArgs<T> &a, const T *src, int ptx0, int pty0)
+{
+    using TL = Step2Tile<T>;
+    constexpr int LINE = 128 / (int)sizeof(T), LINES = TL::TX / LINE;          // 128-byte lines per tile row
+    if (pty0 < 1 || pty0 + TL::TY + 1 > a.H || ptx0 < 0 || ptx0 + TL::TX > a.W) return;
+    static_assert(TL::EY * LINES <= TL::NT, "one thread per (row, line) of the tile");
+    if (threadIdx.x >= TL::EY * LINES) return;       // the first EY*LINES threads: one line of all nine populations each
+    const int r = threadIdx.x / LINES, l = threadIdx.x % LINES;
+    const char *p = reinterpret_cast<const char *>(src + (size_t)(pty0 - 1 + GHOST + r) * a.pitch + ptx0 + l * LINE);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) asm volatile("prefetch.global.L2 [%0];" : : "l"(p + a.st_off[q]));
+}
+
 // One tile: rows [ty0, ty0+TY) x columns [tx0, tx0+TX); rows >= y_end are not stored (tile rows
 // that overlap the next region).  P2P: also deliver the face rows to the neighbours.
 template <typename T, bool PERIODIC_X, int COL, bool P2P, bool USE_MASK>
@@ -210,10 +230,17 @@ step2_kernel(const __grid_constant__ StepArgs<T> a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     asm volatile("griddepcontrol.launch_dependents;");
     const int y_end = a.y_begin + a.y_count;
-    const int ty0 = a.y_begin + (blockIdx.z * gridDim.y + blockIdx.y) * TL::TY;
+    const int trow = blockIdx.z * gridDim.y + blockIdx.y;
+    const int ty0 = a.y_begin + trow * TL::TY;
     if (ty0 >= y_end) return;
-    step2_tile<T, PERIODIC_X, COL, false, USE_MASK>(a, reinterpret_cast<T *>(smem_raw), blockIdx.x * TL::TX, ty0, y_end,
-                                                    order_after_grid_dependency());
+    const int tok = order_after_grid_dependency();
+    if (a.prefetch_tiles > 0) {
+        int pcol = blockIdx.x + a.prefetch_cols, prow = trow + a.prefetch_rows;
+        if (pcol >= (int)gridDim.x) { pcol -= gridDim.x; prow += 1; }
+        const int pty0 = a.y_begin + prow * TL::TY;
+        if (pty0 + TL::TY <= y_end) step2_prefetch_tile(a, a.src + tok, pcol * TL::TX, pty0);
+    }
+    step2_tile<T, PERIODIC_X, COL, false, USE_MASK>(a, reinterpret_cast<T *>(smem_raw), blockIdx.x * TL::TX, ty0, y_end, tok);
 }
 
 // a whole y-slab, H >= 2 TY: tile-row slot 0 -> rows [0, TY), slot 1 -> rows [H-TY, H) (the two face
@@ -231,7 +258,14 @@ step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     if (slot >= 2) {                                 // interior tile row: no ghost row, feeds no neighbour
         const int ty0 = (slot - 1) * TL::TY;
         if (ty0 >= a.H - TL::TY) return;
-        step2_tile<T, PERIODIC_X, COL, false, USE_MASK>(a, sm, tx0, ty0, a.H - TL::TY, order_after_grid_dependency());
+        const int tok = order_after_grid_dependency();
+        if (a.prefetch_tiles > 0) {                  // a later interior tile (slot' >= 2 as well)
+            int pcol = blockIdx.x + a.prefetch_cols, pslot = slot + a.prefetch_rows;
+            if (pcol >= (int)gridDim.x) { pcol -= gridDim.x; pslot += 1; }
+            const int pty0 = (pslot - 1) * TL::TY;
+            if (pty0 + TL::TY <= a.H - TL::TY) step2_prefetch_tile(a, a.src + tok, pcol * TL::TX, pty0);
+        }
+        step2_tile<T, PERIODIC_X, COL, false, USE_MASK>(a, sm, tx0, ty0, a.H - TL::TY, tok);
         return;
     }
     const HaloP2P &p = a.halo;
@@ -241,6 +275,24 @@ step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) publish_step(p, 2u * gridDim.x, 2u);
+}
+
+// tiles ahead for the L2 prefetch: CHEMSIM_LBM_PREFETCH=<n> in the environment (0 = off); default one wave
+// (resident blocks per SM x SMs of the device)
+template <typename T>
+int step2_prefetch_tiles()
+{
+    static const int n = [] {
+        if (const char *e = getenv("CHEMSIM_LBM_PREFETCH")) return atoi(e);
+        return CHEMSIM_STEP2_PREFETCH_DEFAULT;
+    }();
+    if (n >= 0) return n;
+    static const int sms = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return -n * Step2Tile<T>::BLOCKS * sms;           // -1: one wave, -2: two waves
 }
 
 template <typename K>
@@ -254,11 +306,15 @@ void step2_opt_in(K kernel, size_t smem)
 
 // rows [y_begin, y_begin + y_count) advance by TWO steps; y_count need not be a multiple of the tile height
 template <typename T, int COL>
-void launch_step2_col(const StepArgs<T> &a, cudaStream_t s)
+void launch_step2_col(const StepArgs<T> &a_in, cudaStream_t s)
 {
     using TL = Step2Tile<T>;
     const dim3 block(TL::NT);
-    const dim3 grid = row_grid((a.W + TL::TX - 1) / TL::TX, (a.y_count + TL::TY - 1) / TL::TY);
+    const dim3 grid = row_grid((a_in.W + TL::TX - 1) / TL::TX, (a_in.y_count + TL::TY - 1) / TL::TY);
+    StepArgs<T> a = a_in;
+    a.prefetch_tiles = step2_prefetch_tiles<T>();
+    a.prefetch_rows = a.prefetch_tiles / (int)grid.x;
+    a.prefetch_cols = a.prefetch_tiles % (int)grid.x;
     // a region at a slab face recomputes ghost-row cells, whose solid flags the neighbour owns
     const bool masked = a.has_mask != 0 || (a.ghost_mask != 0 && (a.y_begin == 0 || a.y_begin + a.y_count >= a.H));
 #define CHEMSIM_LAUNCH_STEP2(PX, M)                                                           \
@@ -273,12 +329,16 @@ void launch_step2_col(const StepArgs<T> &a, cudaStream_t s)
 
 // the whole slab, two steps, with the peer-memory halo (H >= 2 TY)
 template <typename T, int COL>
-void launch_slab_p2p2_col(const StepArgs<T> &a, cudaStream_t s)
+void launch_slab_p2p2_col(const StepArgs<T> &a_in, cudaStream_t s)
 {
     using TL = Step2Tile<T>;
     const dim3 block(TL::NT);
-    const int interior_rows = a.H - 2 * TL::TY;
-    const dim3 grid = row_grid((a.W + TL::TX - 1) / TL::TX, 2 + (interior_rows + TL::TY - 1) / TL::TY);
+    const int interior_rows = a_in.H - 2 * TL::TY;
+    const dim3 grid = row_grid((a_in.W + TL::TX - 1) / TL::TX, 2 + (interior_rows + TL::TY - 1) / TL::TY);
+    StepArgs<T> a = a_in;
+    a.prefetch_tiles = step2_prefetch_tiles<T>();
+    a.prefetch_rows = a.prefetch_tiles / (int)grid.x;
+    a.prefetch_cols = a.prefetch_tiles % (int)grid.x;
 #define CHEMSIM_LAUNCH_STEP2(PX, M)                                                           \
     do {                                                                                      \
         step2_opt_in(step2_slab_p2p_kernel<T, PX, COL, M>, TL::SMEM);                         \

@@ -30,6 +30,10 @@ constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 #ifndef CHEMSIM_PACKED_VEC
 #define CHEMSIM_PACKED_VEC 0
 #endif
+// two-step kernels: L2 prefetch distance in tiles (>= 0), or in waves of resident blocks (-1, -2); 0 = off
+#ifndef CHEMSIM_STEP2_PREFETCH_DEFAULT
+#define CHEMSIM_STEP2_PREFETCH_DEFAULT 0
+#endif
 template <int COL> __host__ __device__ constexpr bool vec_packed() { return ((CHEMSIM_PACKED_VEC >> COL) & 1) != 0; }
 
 // widths that are a multiple of the vector width take the 128-bit kernels

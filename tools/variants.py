@@ -16,6 +16,7 @@ VARIANTS = {
     "s2ty8": ["CHEMSIM_STEP2_TY=8"],         # two-step kernel: 8-row tiles (256 threads, 4 blocks/SM, rim +27 %)
     "s2ty32": ["CHEMSIM_STEP2_TY=32"],       # 32-row tiles (1024 threads, 1 block/SM, rim +8 %)
     "scalar": ["CHEMSIM_PACKED_STEP2=0"],    # two-step kernels without the packed f32 additions (the r02 build before F32x2)
+    "pm": ["CHEMSIM_PACKED_MUL=1"],          # packed multiplications too (fma.rn.f32x2 with an opaque -0 addend, d2q9.cuh)
     "vp": ["CHEMSIM_PACKED_VEC=0x1e"],       # single-step vector kernels packed too, 64-register cap (spills)
     "vp3": ["CHEMSIM_PACKED_VEC=0x1e", "CHEMSIM_STEP_MIN_BLOCKS=3", "CHEMSIM_KBC_MIN_BLOCKS=3"],   # ... at 80 registers
     "vp2": ["CHEMSIM_PACKED_VEC=0x1e", "CHEMSIM_STEP_MIN_BLOCKS=2", "CHEMSIM_KBC_MIN_BLOCKS=2"],   # ... at 128 registers
