@@ -10,7 +10,7 @@
 //
 //   phase A  (TY+2) x (TX+2) cells ("ext" region): one cell per thread and iteration (two in
 //            flight), scalar coalesced loads from HBM/L2; results go to smem[q][row][col + shift_q].
-//            The rim is redundant work (+14 % cells for the 16 x 128 tile) whose loads hit L2 (the
+//            The rim is redundant work (+27 % cells for the 8 x 128 tile) whose loads hit L2 (the
 //            neighbouring tiles read the same lines).
 //   phase B  one warp per tile row, V = 16/sizeof(T) cells per lane: nine aligned 128-bit
 //            shared-memory loads (the per-population column shift_q makes every shifted read
@@ -277,8 +277,8 @@ step2_slab_p2p_kernel(const __grid_constant__ StepArgs<T> a)
     if (threadIdx.x == 0) publish_step(p, 2u * gridDim.x, 2u);
 }
 
-// tiles ahead for the L2 prefetch: CHEMSIM_LBM_PREFETCH=<n> in the environment (0 = off); default one wave
-// (resident blocks per SM x SMs of the device)
+// tiles ahead for the L2 prefetch: CHEMSIM_LBM_PREFETCH=<n> in the environment overrides the build's default
+// (n > 0: tiles, n < 0: percent of one wave = resident blocks per SM x SMs of the device, 0: off)
 template <typename T>
 int step2_prefetch_tiles()
 {
@@ -292,7 +292,7 @@ int step2_prefetch_tiles()
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         return v;
     }();
-    return -n * Step2Tile<T>::BLOCKS * sms;           // -1: one wave, -2: two waves
+    return (int)((long long)-n * Step2Tile<T>::BLOCKS * sms / 100);
 }
 
 template <typename K>

@@ -30,9 +30,11 @@ constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 #ifndef CHEMSIM_PACKED_VEC
 #define CHEMSIM_PACKED_VEC 0
 #endif
-// two-step kernels: L2 prefetch distance in tiles (>= 0), or in waves of resident blocks (-1, -2); 0 = off
+// two-step kernels: L2 prefetch distance in tiles (> 0), or in percent of one wave of resident blocks
+// (< 0: -100 = one wave, -50 = half a wave); 0 = off.  Measured (r02n, TY = 16): half a wave +3.8 %, one
+// wave -1.3 %, two waves -10 % (the prefetched lines are evicted again before they are used).
 #ifndef CHEMSIM_STEP2_PREFETCH_DEFAULT
-#define CHEMSIM_STEP2_PREFETCH_DEFAULT 0
+#define CHEMSIM_STEP2_PREFETCH_DEFAULT -50
 #endif
 template <int COL> __host__ __device__ constexpr bool vec_packed() { return ((CHEMSIM_PACKED_VEC >> COL) & 1) != 0; }
 
@@ -52,11 +54,13 @@ template <typename T>
 struct Step2Tile {
     static constexpr int V = VecOf<T>::N;          // cells per 16 bytes
     static constexpr int TX = 32 * V;              // one warp covers a tile row in phase B
-    // tile height (tools/variants.py s2ty8 / s2ty32 override it).  Measured on 4096^2 BGK, GLUPS f32 / f64:
-    // TY = 8: 125.9 / 69.6, TY = 16: 124.7 / 66.2, TY = 32: 115.7 / 58.9 (one block per SM: the phases of
-    // different blocks no longer overlap).  f32 is power-capped either way (TY = 8 runs at lower clocks).
+    // tile height (tools/variants.py s2ty16 / s2ty32 override it).  Measured on 4096^2 BGK, GLUPS f32 / f64:
+    //   before the packed additions:  TY = 8: 125.9 / 69.6, TY = 16: 124.7 / 66.2, TY = 32: 115.7 / 58.9
+    //   with them (r02n):             TY = 8: 132.7 (137.0 in 20-step batches, below the power cap), TY = 16: 128.9 (128.7)
+    // Four 256-thread blocks per SM overlap their load / barrier / store phases better than two 512-thread
+    // blocks; the taller rim of the flat tile (+27 % cells instead of +14 %) is cheaper than that.
 #ifndef CHEMSIM_STEP2_TY
-#define CHEMSIM_STEP2_TY (sizeof(T) == 8 ? 8 : 16)
+#define CHEMSIM_STEP2_TY 8
 #endif
     static constexpr int TY = CHEMSIM_STEP2_TY;
     static constexpr int NT = 32 * TY;             // threads per block: one warp per tile row

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": [],
     "bulk": ["CHEMSIM_EXPERIMENT_BULK"],     # TMA bulk-copy loads (step_bulk_experiment.cuh); run with CHEMSIM_LBM_BULK=1 CHEMSIM_LBM_STEP2=0
-    "s2ty8": ["CHEMSIM_STEP2_TY=8"],         # two-step kernel: 8-row tiles (256 threads, 4 blocks/SM, rim +27 %)
+    "s2ty16": ["CHEMSIM_STEP2_TY=16"],       # two-step kernel: 16-row tiles (512 threads, 2 blocks/SM, rim +14 %); default is 8
     "s2ty32": ["CHEMSIM_STEP2_TY=32"],       # 32-row tiles (1024 threads, 1 block/SM, rim +8 %)
     "scalar": ["CHEMSIM_PACKED_STEP2=0"],    # two-step kernels without the packed f32 additions (the r02 build before F32x2)
     "pm": ["CHEMSIM_PACKED_MUL=1"],          # packed multiplications too (fma.rn.f32x2 with an opaque -0 addend, d2q9.cuh)
