@@ -31,10 +31,13 @@ constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 #define CHEMSIM_PACKED_VEC 0
 #endif
 // two-step kernels: L2 prefetch distance in tiles (> 0), or in percent of one wave of resident blocks
-// (< 0: -100 = one wave, -50 = half a wave); 0 = off.  Measured (r02n, TY = 16): half a wave +3.8 %, one
-// wave -1.3 %, two waves -10 % (the prefetched lines are evicted again before they are used).
+// (< 0: -100 = one wave, -25 = a quarter); 0 = off.  Measured on 4096^2 BGK f32 (r02o, TY = 8, wave = 592 tiles),
+// GLUPS in 200-step batches (power-capped) / 20-step batches: off 128.9 / 137.3, 64 tiles 133.9, 148 tiles
+// 133.7 / 151.0, 296 tiles 132.2 / 143.6, 444 tiles 130.2; f64: off 69.9, 148 tiles 75.0, 296 tiles 73.7.
+// Further ahead the lines are evicted again before they are used (r02n, one wave at TY = 16: DRAM reads
+// 604 -> 753 MB per launch, -1.3 %; two waves -10 %).
 #ifndef CHEMSIM_STEP2_PREFETCH_DEFAULT
-#define CHEMSIM_STEP2_PREFETCH_DEFAULT -50
+#define CHEMSIM_STEP2_PREFETCH_DEFAULT -25
 #endif
 template <int COL> __host__ __device__ constexpr bool vec_packed() { return ((CHEMSIM_PACKED_VEC >> COL) & 1) != 0; }
 
