@@ -76,8 +76,11 @@ __device__ __forceinline__ double root(double a)          { return __dsqrt_rn(a)
 // values of this type: every addition/subtraction is one packed instruction.  The
 // MULTIPLICATIONS stay scalar on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
 // even with explicit .rn and --fmad=false (seen in SASS, CUDA 12.9), which would change the
-// rounding; a scalar mul.rn.f32 feeding a packed add is never contracted.  tools/sass_count.py
-// --no-ffma2 checks that the built kernels contain no FFMA2 at all.
+// rounding; a scalar mul.rn.f32 feeding a packed add is never contracted.
+// tests/test_abi.py::test_packed_f32_additions_are_never_contracted checks the built library's SASS
+// (no FFMA2 / FMUL2 anywhere), tests/test_host_arith.py the F32x2 instantiation of the operators on the CPU.
+// FADD2 issues at half rate (same FP32 pipe time as two FADDs): what it saves are issue slots —
+// measured +1.7 % (BGK) to +3.2 % (Regularized) on the two-step kernels (profiles/r02_packed_prefetch_ab.md).
 struct F32x2 {
     float lo, hi;
     F32x2() = default;
@@ -101,7 +104,8 @@ struct F32x2 {
 CHEMSIM_F32X2_OP(add, "add", __fadd_rn)
 CHEMSIM_F32X2_OP(sub, "sub", __fsub_rn)
 #undef CHEMSIM_F32X2_OP
-// -DCHEMSIM_PACKED_MUL=1: packed multiplications after all, written as fma.rn.f32x2(a, b, -0) with the
+// -DCHEMSIM_PACKED_MUL=1 (tools/variants.py pm; measured SLOWER, 125.5 vs 128.9 GLUPS: spills, constants forced
+// into vector registers — not the default): packed multiplications after all, written as fma.rn.f32x2(a, b, -0) with the
 // -0 read from constant memory, i.e. opaque to ptxas.  RN(a*b + (-0)) == RN(a*b) for every a, b
 // (a zero product keeps its sign: (+0) + (-0) = +0, (-0) + (-0) = -0; inf*0 stays NaN), and an FMA
 // cannot be contracted any further with the addition that consumes it.

@@ -8,13 +8,16 @@
 // rounded operations, and the intermediate is held in the lattice dtype exactly as the A-B buffer
 // would hold it, so two passes of the single-step kernel and one pass of this one are bit-identical.
 //
-//   phase A  (TY+2) x (TX+2) cells ("ext" region): one cell per thread and iteration (two in
-//            flight), scalar coalesced loads from HBM/L2; results go to smem[q][row][col + shift_q].
+//   phase A  (TY+2) x (TX+2) cells ("ext" region): one cell per thread and iteration (f32: two in
+//            flight, collided together with packed additions, see F32x2 in d2q9.cuh), scalar
+//            coalesced loads from HBM/L2; results go to smem[q][row][col + shift_q].
 //            The rim is redundant work (+27 % cells for the 8 x 128 tile) whose loads hit L2 (the
 //            neighbouring tiles read the same lines).
 //   phase B  one warp per tile row, V = 16/sizeof(T) cells per lane: nine aligned 128-bit
 //            shared-memory loads (the per-population column shift_q makes every shifted read
 //            start on a 16-byte boundary: conflict-free), collide, nine 128-bit global stores.
+//   prefetch every block first asks L2 for the source lines of the tile a quarter of a wave further
+//            down the dispatch order (step2_prefetch_tile), so that block's first loads hit L2.
 //
 // Edges: cells outside a zero-fill lattice hold 0 in the ext region (they are never computed:
 // src/lbm.rs:716-729 drops what leaves the array); periodic edges wrap the coordinates.  On a
