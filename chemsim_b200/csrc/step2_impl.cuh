@@ -86,7 +86,48 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
         unsigned long long base = reinterpret_cast<unsigned long long>(src) +
                                   ((size_t)(ty0 - 1 + GHOST) * a.pitch + (tx0 - 1)) * sizeof(T);
         asm volatile("" : "+l"(base));
-        if constexpr (sizeof(T) == 4) {
+        if constexpr (sizeof(T) == 4 && CHEMSIM_STEP2_HPAIR != 0) {
+            // f32, variant: each thread takes two HORIZONTALLY adjacent ext cells (2 px, 2 px + 1).  The second cell's
+            // addresses are the first one's + 4 bytes (no address arithmetic of its own), and because the ext region
+            // starts at an odd column (tx0 - 1) the six populations that stream along x sit on an 8-byte boundary:
+            // one 64-bit load each, straight into the register pair the packed collision works on.  In shared
+            // memory the same six land on even columns (shift_q even): one 64-bit store each.
+            static_assert(EX % 2 == 0 && SP % 2 == 0 && (EY * SP) % 2 == 0, "pairs must not straddle rows");
+            constexpr int PX = EX / 2, DYP = NT / PX, DXP = NT % PX;
+            int ey0 = tid / PX, px0 = tid - ey0 * PX;
+#pragma unroll 1
+            for (int idx = tid; idx < EY * PX; idx += NT) {
+                const char *p0 = reinterpret_cast<const char *>(base) + ((size_t)ey0 * a.pitch + 2 * px0) * sizeof(T);
+                T c0[Q], c1[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const char *sp = p0 + (a.ld_off[q] - ex_of(q) * (long long)sizeof(T));
+                    if (ex_of(q) != 0) {
+                        const float2 v = __ldg(reinterpret_cast<const float2 *>(sp));
+                        c0[q] = v.x; c1[q] = v.y;
+                    } else {
+                        c0[q] = __ldg(reinterpret_cast<const T *>(sp));
+                        c1[q] = __ldg(reinterpret_cast<const T *>(sp + sizeof(T)));
+                    }
+                }
+                if (use_mask) {
+                    const uint8_t *mp = mask + (size_t)(ty0 - 1 + ey0) * a.mask_pitch + (tx0 - 1 + 2 * px0);
+                    const bool s0 = __ldg(mp) != 0, s1 = __ldg(mp + 1) != 0;
+                    bounce_back(c0, s0);
+                    bounce_back(c1, s1);
+                }
+                collide2<COL, CHEMSIM_PACKED_STEP2 != 0>(c0, c1, a.k);
+                T *d0 = sm + ey0 * SP + 2 * px0;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    T *dq = d0 + q * (EY * SP) + shift_of<V>(q);
+                    if (shift_of<V>(q) % 2 == 0) *reinterpret_cast<float2 *>(dq) = make_float2(c0[q], c1[q]);
+                    else { dq[0] = c0[q]; dq[1] = c1[q]; }
+                }
+                ey0 += DYP; px0 += DXP;
+                if (px0 >= PX) { px0 -= PX; ey0 += 1; }
+            }
+        } else if constexpr (sizeof(T) == 4) {
             // f32: two ext cells per iteration, all eighteen loads issued before the first collision —
             // the HBM/L2 latency of one cell is covered by the arithmetic of the other
 #pragma unroll 1

@@ -30,6 +30,11 @@ constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 #ifndef CHEMSIM_PACKED_VEC
 #define CHEMSIM_PACKED_VEC 0
 #endif
+// two-step kernels, f32 phase A: 1 = each thread takes two horizontally adjacent cells (64-bit loads / stores where
+// aligned, half the address arithmetic), 0 = two cells a block-width apart (tools/variants.py hpair)
+#ifndef CHEMSIM_STEP2_HPAIR
+#define CHEMSIM_STEP2_HPAIR 0
+#endif
 // two-step kernels: L2 prefetch distance in tiles (> 0), or in percent of one wave of resident blocks
 // (< 0: -100 = one wave, -25 = a quarter); 0 = off.  Measured on 4096^2 BGK f32 (r02o, TY = 8, wave = 592 tiles),
 // GLUPS in 200-step batches (power-capped) / 20-step batches: off 128.9 / 137.3, 64 tiles 133.9, 148 tiles
