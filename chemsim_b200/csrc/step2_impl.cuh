@@ -261,7 +261,14 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
     }
     char *out = reinterpret_cast<char *>(a.dst) + ((size_t)(gy + GHOST) * a.pitch + gx0) * sizeof(T);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) store_vec(reinterpret_cast<T *>(out + a.st_off[q]), g[q]);
+    for (int q = 0; q < Q; ++q) {
+        if constexpr (CHEMSIM_STEP2_STORE_CS != 0) {
+            if constexpr (V == 4) __stcs(reinterpret_cast<float4 *>(out + a.st_off[q]), make_float4(g[q][0], g[q][1], g[q][2], g[q][3]));
+            else                  __stcs(reinterpret_cast<double2 *>(out + a.st_off[q]), make_double2(g[q][0], g[q][1]));
+        } else {
+            store_vec(reinterpret_cast<T *>(out + a.st_off[q]), g[q]);
+        }
+    }
     if (P2P) halo_store_row(a, gy, gx0, g);
 }
 

@@ -31,9 +31,15 @@ constexpr int STEP_THREADS = CHEMSIM_STEP_THREADS;
 #define CHEMSIM_PACKED_VEC 0
 #endif
 // two-step kernels, f32 phase A: 1 = each thread takes two horizontally adjacent cells (64-bit loads / stores where
-// aligned, half the address arithmetic), 0 = two cells a block-width apart (tools/variants.py hpair)
+// aligned, half the address arithmetic), 0 = two cells a block-width apart (tools/variants.py nohpair).  Measured
+// (r02t, 4096^2 BGK): 157.0 vs 143.9 GLUPS in 20-step batches, 140.7 vs 131.5 sustained.
 #ifndef CHEMSIM_STEP2_HPAIR
-#define CHEMSIM_STEP2_HPAIR 0
+#define CHEMSIM_STEP2_HPAIR 1
+#endif
+// two-step kernels, phase B: 1 = streaming stores (st.global.cs: the result is not read again before the next pass,
+// which leaves more of L2 to the prefetched source lines), 0 = default write-back stores
+#ifndef CHEMSIM_STEP2_STORE_CS
+#define CHEMSIM_STEP2_STORE_CS 1
 #endif
 // two-step kernels: L2 prefetch distance in tiles (> 0), or in percent of one wave of resident blocks
 // (< 0: -100 = one wave, -25 = a quarter); 0 = off.  Measured on 4096^2 BGK f32 (r02o, TY = 8, wave = 592 tiles),

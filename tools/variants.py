@@ -13,7 +13,8 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": [],
     "bulk": ["CHEMSIM_EXPERIMENT_BULK"],     # TMA bulk-copy loads (step_bulk_experiment.cuh); run with CHEMSIM_LBM_BULK=1 CHEMSIM_LBM_STEP2=0
-    "hpair": ["CHEMSIM_STEP2_HPAIR=1"],      # f32 phase A on horizontally adjacent cell pairs (64-bit loads/stores)
+    "nohpair": ["CHEMSIM_STEP2_HPAIR=0"],    # f32 phase A on two cells a block-width apart (scalar loads/stores) instead of adjacent pairs
+    "nostcs2": ["CHEMSIM_STEP2_STORE_CS=0"], # two-step phase B with write-back stores instead of streaming stores
     "s2ty10": ["CHEMSIM_STEP2_TY=10"],       # 10-row tiles (320 threads, 3 blocks/SM, rim +22 %)
     "s2ty16": ["CHEMSIM_STEP2_TY=16"],       # two-step kernel: 16-row tiles (512 threads, 2 blocks/SM, rim +14 %); default is 8
     "s2ty32": ["CHEMSIM_STEP2_TY=32"],       # 32-row tiles (1024 threads, 1 block/SM, rim +8 %)
