@@ -29,7 +29,7 @@ def run_worker(w, rows_per_rank, edge, dtype, halo, extra_rows=1):
     assert "MULTIGPU_OK" in res.stdout
 
 
-# (width, rows per rank, edge, dtype): slabs of >= 32 rows advance two steps per pass, smaller ones one;
+# (width, rows per rank, edge, dtype): slabs of >= 16 rows (two 8-row tiles) advance two steps per pass, smaller ones one;
 # 37 is a ragged width (scalar kernel), 260 a vector width that ends mid-warp
 @pytest.mark.parametrize("w,rows,edge,dtype", [(256, 48, 1, "f32"), (260, 25, 0, "f64"), (1024, 33, 1, "f64"),
                                                (37, 10, 1, "f32"), (2048, 40, 0, "f32"), (512, 2, 1, "f32")])
