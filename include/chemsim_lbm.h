@@ -28,6 +28,14 @@
  *    asynchronous and ordered with later calls.
  *  - There is no CPU fallback: without a CUDA device every compute entry point
  *    fails with CHEMSIM_LBM_ERR_CUDA.
+ *
+ * Environment switches (read once per process; none of them changes a result —
+ * they select between bit-identical execution strategies for A/B measurements):
+ *    CHEMSIM_LBM_STEP2=0          every step on the single-step kernels (default: two steps per pass)
+ *    CHEMSIM_LBM_PREFETCH=<n>     two-step kernels: L2 prefetch distance in tiles (0 = off; default a quarter
+ *                                 of a wave of resident blocks; n < 0: percent of a wave)
+ *    CHEMSIM_LBM_PDL=0            plain stream order instead of programmatic dependent launch
+ *    CHEMSIM_LBM_P2P_TIMEOUT_S=<s> how long a face block waits for a neighbour GPU's step flag
  */
 #ifndef CHEMSIM_LBM_H
 #define CHEMSIM_LBM_H
