@@ -8,9 +8,10 @@
 // rounded operations, and the intermediate is held in the lattice dtype exactly as the A-B buffer
 // would hold it, so two passes of the single-step kernel and one pass of this one are bit-identical.
 //
-//   phase A  (TY+2) x (TX+2) cells ("ext" region): one cell per thread and iteration (f32: two in
-//            flight, collided together with packed additions, see F32x2 in d2q9.cuh), scalar
-//            coalesced loads from HBM/L2; results go to smem[q][row][col + shift_q].
+//   phase A  (TY+2) x (TX+2) cells ("ext" region): f64 one cell per thread and iteration, scalar
+//            coalesced loads; f32 one pair of horizontally adjacent cells (64-bit loads and
+//            shared-memory stores where the pair is 8-byte aligned), collided together with packed
+//            additions (F32x2 in d2q9.cuh); results go to smem[q][row][col + shift_q].
 //            The rim is redundant work (+27 % cells for the 8 x 128 tile) whose loads hit L2 (the
 //            neighbouring tiles read the same lines).
 //   phase B  one warp per tile row, V = 16/sizeof(T) cells per lane: nine aligned 128-bit
@@ -87,7 +88,7 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
                                   ((size_t)(ty0 - 1 + GHOST) * a.pitch + (tx0 - 1)) * sizeof(T);
         asm volatile("" : "+l"(base));
         if constexpr (sizeof(T) == 4 && CHEMSIM_STEP2_HPAIR != 0) {
-            // f32, variant: each thread takes two HORIZONTALLY adjacent ext cells (2 px, 2 px + 1).  The second cell's
+            // f32: each thread takes two HORIZONTALLY adjacent ext cells (2 px, 2 px + 1).  The second cell's
             // addresses are the first one's + 4 bytes (no address arithmetic of its own), and because the ext region
             // starts at an odd column (tx0 - 1) the six populations that stream along x sit on an 8-byte boundary:
             // one 64-bit load each, straight into the register pair the packed collision works on.  In shared
@@ -128,7 +129,8 @@ __device__ __forceinline__ void step2_tile(const StepArgs<T> &a, T *const sm, co
                 if (px0 >= PX) { px0 -= PX; ey0 += 1; }
             }
         } else if constexpr (sizeof(T) == 4) {
-            // f32: two ext cells per iteration, all eighteen loads issued before the first collision —
+            // f32 with CHEMSIM_STEP2_HPAIR=0 (the earlier form, kept for A/B): two ext cells a block-width apart per
+            // iteration, all eighteen loads issued before the first collision —
             // the HBM/L2 latency of one cell is covered by the arithmetic of the other
 #pragma unroll 1
             for (int idx = tid; idx < EY * EX; idx += 2 * NT) {
