@@ -25,7 +25,7 @@ for line in sass.splitlines():
         m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
         if m:
             ops[name][m.group(1)] += 1
-FP = ("FADD", "FMUL", "FFMA", "DADD", "DMUL", "DFMA", "MUFU", "FSEL", "FSETP", "DSETP", "FMNMX", "FCHK")
+FP = ("FADD", "FMUL", "FFMA", "FADD2", "FMUL2", "FFMA2", "DADD", "DMUL", "DFMA", "MUFU", "FSEL", "FSETP", "DSETP", "FMNMX", "FCHK")
 INT = ("IADD3", "IMAD", "LEA", "SHF", "LOP3", "ISETP", "SEL", "MOV", "IADD", "UIADD3", "UIMAD", "ULEA", "USHF", "UMOV",
        "UISETP", "ULOP3", "PRMT", "CS2R", "HFMA2", "I2F", "F2I", "PLOP3", "USEL", "IABS", "UFLO", "R2UR", "S2R", "S2UR")
 MEM = ("LDG", "STG", "LDC", "LDCU", "ULDC", "SHFL", "LDS", "STS")
